@@ -1,0 +1,196 @@
+/* mtvaf_b200 -- C ABI of the B200-native (sm_100a) MTVAF hot path.
+ *
+ * The reference (MKMaS-GUET/MTVAF) has NO plugin/operator/FFI interface: the path sits behind plain
+ * torch nn.Module classes.  The drop-in boundary is therefore the Python class
+ * surface in mtvaf_b200/ (same class names, ctor and forward signatures as models/bert_model.py,
+ * models/modeling_roberta.py, models/modeling_bert.py, probes/), and THIS header is the thin C ABI those
+ * classes call through ctypes -- one entry point per ATen call-site group of the reference, cited
+ * below as file:line of the reference code each one replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (torch allocations) unless
+ * noted; all functions are stream-ordered on `stream` (a cudaStream_t passed as void*), allocate
+ * nothing, never synchronise and never throw: they return 0 on success or a negative code
+ * (-1 bad argument, -2 CUDA error) with the message available from mtvaf_last_error().
+ * dtype codes: MTVAF_F32 = 0 (parity mode: fp32 storage, fp32 SIMT math), MTVAF_BF16 = 1
+ * (throughput mode: bf16 storage, tcgen05 tensor-core GEMMs with fp32 accumulation).
+ */
+#ifndef MTVAF_B200_H_
+#define MTVAF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTVAF_ABI_VERSION 1
+#define MTVAF_F32 0
+#define MTVAF_BF16 1
+
+/* ---- library ------------------------------------------------------------------------------- */
+int mtvaf_abi_version(void);
+const char* mtvaf_last_error(void);
+/* fills sm count and compute capability of the current device */
+int mtvaf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- GEMM family --------------------------------------------------------------------------- */
+/* D[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) ).
+ * Operand storage: `a_mn_major == 0`: A is [M,K] row-major (K contiguous, leading dim lda);
+ *                  `a_mn_major == 1`: A is stored [K,M] (M contiguous, leading dim lda).
+ *                  same for B with N in place of M.
+ *   forward  Y = X W^T      (nn.Linear; modeling_roberta.py:202,219-220,296,365,379): A K-major, B K-major
+ *   dgrad    dX = dY W      : A K-major, B MN-major
+ *   wgrad    dW = dY^T X    : A MN-major, B MN-major
+ */
+enum {
+  MTVAF_EPI_STORE = 0,      /* out = acc (+bias)                                                  */
+  MTVAF_EPI_GELU = 1,       /* out2 = acc+bias (pre-activation, optional); out = gelu_erf(out2)   */
+  MTVAF_EPI_TANH = 2,       /* out = tanh(acc+bias)                        (bert_model.py:446-454) */
+  MTVAF_EPI_RESID = 3,      /* out = dropout(acc+bias) + aux               (modeling_roberta.py:296-298 minus LN) */
+  MTVAF_EPI_ATOMIC_F32 = 4, /* out(f32) += acc   (split-K weight gradients into the grad bucket)   */
+  MTVAF_EPI_MUL_DGELU = 5,  /* out = acc * gelu_erf'(aux)                  (backward of :365-366)  */
+  MTVAF_EPI_MUL_DTANH = 6,  /* out = acc * (1 - aux^2)                                             */
+  MTVAF_EPI_SQNORM = 7,     /* rowsum[m] += sum_n acc^2 ; out (optional) = acc   (probes/probe.py:74-78) */
+  MTVAF_EPI_ROWSCALE = 8    /* out = acc * rowscale[m]  (probe backward: 2 g_m T_m)                */
+};
+
+typedef struct MtvafEpilogue {
+  int32_t mode;            /* MTVAF_EPI_*                                                         */
+  int32_t out_dtype;       /* MTVAF_F32 / MTVAF_BF16 of `out` and `out2` (ATOMIC_F32: ignored)     */
+  void* out;               /* [M, ldo]                                                            */
+  int64_t ldo;
+  const float* bias;       /* [N] fp32 or NULL                                                    */
+  const void* aux;         /* residual / pre-activation / tanh output, same dtype as the operands */
+  int64_t ld_aux;
+  void* out2;              /* optional second output (pre-GELU), dtype out_dtype                  */
+  int64_t ld_out2;
+  float* rowvec;           /* SQNORM: [M] fp32 accumulated with atomics; ROWSCALE: [M] fp32 input  */
+  float alpha;             /* scale applied to the accumulator first (1.0 = none)                 */
+  float p_drop;            /* RESID: dropout probability (0 = off)                                */
+  uint64_t seed;           /* RESID: dropout stream seed; element index = m * N + n               */
+} MtvafEpilogue;
+
+/* bf16 operands, tcgen05.mma (kind::f16) with TMEM fp32 accumulators, TMA-fed, persistent.
+ * Requirements: lda/ldb multiples of 8 elements, A/B base pointers 16-byte aligned.
+ * `splits` > 1 partitions K over CTAs (only with MTVAF_EPI_ATOMIC_F32 / SQNORM is that meaningful). */
+int mtvaf_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                    int M, int N, int K, const MtvafEpilogue* epi, int splits, void* stream);
+/* fp32 operands, fp32 FFMA (parity mode; also used for skinny heads such as fc 768->11). */
+int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                   int M, int N, int K, const MtvafEpilogue* epi, int splits, void* stream);
+
+/* ---- elementwise / reductions --------------------------------------------------------------- */
+int mtvaf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int mtvaf_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* db[n] += sum_m dY[m,n]   (bias gradients; fp32 atomics into the grad bucket) */
+int mtvaf_colsum(const void* dy, int64_t ld, int dtype, int M, int N, float* db, void* stream);
+
+/* ---- embeddings: RobertaEmbeddings.forward modeling_roberta.py:102-140 (+ :1706-1719),
+ *      BertEmbeddings.forward modeling_bert.py:188-222 ------------------------------------------- */
+/* kind 0 = roberta (position ids = cumsum(ids != pad) * (ids != pad) + pad, bit-exact int64),
+ * kind 1 = bert (position ids = arange(L)).  Writes position ids (int64 [B,L]), the pre-LN sum is
+ * not kept: mean/rstd [B*L] fp32 are saved for backward.  Dropout p on the output (0 = off). */
+int mtvaf_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const float* word_emb,
+                       const float* pos_emb, const float* type_emb, const float* gamma, const float* beta,
+                       float eps, int kind, int pad_idx, int B, int L, int H, int vocab, int max_pos, int n_types,
+                       void* out, int out_dtype, int64_t* position_ids, float* mean, float* rstd, float p_drop,
+                       uint64_t seed, void* stream);
+/* backward: LN backward + scatter-add into the three tables (fp32 atomics; rows == padding_idx get
+ * no gradient, as nn.Embedding(padding_idx) does: modeling_roberta.py:78,98-100). */
+int mtvaf_embed_ln_bwd(const void* dout, int dtype, const int64_t* input_ids, const int64_t* token_type_ids,
+                       const int64_t* position_ids, const float* word_emb, const float* pos_emb,
+                       const float* type_emb, const float* gamma, const float* mean, const float* rstd, int kind,
+                       int pad_idx, int B, int L, int H, float* d_word, float* d_pos, float* d_type, float* d_gamma,
+                       float* d_beta, float p_drop, uint64_t seed, void* stream);
+
+/* ---- LayerNorm (RobertaSelfOutput/RobertaOutput tails modeling_roberta.py:298,381) ------------ */
+/* y = LN(z) * gamma + beta over rows of H; saves mean/rstd. z already holds dropout(dense)+residual
+ * (fused into the GEMM epilogue MTVAF_EPI_RESID). */
+int mtvaf_layernorm_fwd(const void* z, void* y, const float* gamma, const float* beta, float eps, int rows, int H,
+                        int dtype, float* mean, float* rstd, void* stream);
+/* dz = LN backward (dtype); d_gamma/d_beta accumulated with fp32 atomics.  If `dres_add` is non-NULL
+ * it is added to the result (gradient arriving through the residual branch of the NEXT op). */
+int mtvaf_layernorm_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+                        int rows, int H, int dtype, void* dz, float* d_gamma, float* d_beta, void* stream);
+
+/* ---- prefix ("fusion") attention: RobertaSelfAttention.forward modeling_roberta.py:218-278 ---- */
+/* qkv: [B*L, 3*nh*d] (Q | K | V column blocks, the fused QKV projection output), row stride ld_qkv.
+ * kp, vp: prefix K/V [B, nh, P, d] (may be NULL when P == 0) -- keys/values are the prefix rows
+ * FOLLOWED by the text rows (torch.cat at :221-222), one softmax over P+L keys.
+ * key_mask: [B, L] int64 text attention mask (prefix columns are always visible, bert_model.py:490-492);
+ * masked keys get the additive -10000.0 of modeling_roberta.py:1000.
+ * ctx: [B*L, nh*d] (heads merged, :276-278).  lse: [B, nh, L] fp32 log-sum-exp saved for backward.
+ * probs (optional, may be NULL): [B, nh, L, P+L] fp32 attention probabilities (output_attentions). */
+int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P,
+                        const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx, float* lse,
+                        float* probs, int dtype, float p_drop, uint64_t seed, void* stream);
+/* dqkv: [B*L, 3*nh*d]; dkp/dvp: [B, nh, P, d] fp32 gradient of the prefix (may be NULL);
+ * dsum_scratch: [B, nh, L] fp32 workspace (rowsum(dO * O)). */
+int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void* qkv, int64_t ld_qkv, const void* kp,
+                        const void* vp, int P, const int64_t* key_mask, const void* ctx, int64_t ld_ctx,
+                        const float* lse, int B, int L, int nh, int d, void* dqkv, int64_t ld_dqkv, float* dkp,
+                        float* dvp, float* dsum_scratch, int dtype, float p_drop, uint64_t seed, void* stream);
+
+/* ---- visual prompt gates: get_visual_prompt bert_model.py:566-587 ----------------------------- */
+/* guids: [n_img, B, 4, 8*hid] MLP outputs (encoder_conv), each row viewed as 4 splits of 2*hid.
+ * gate_logits: [n_img*B, n_layers*4] fp32 = all projectors[l] applied to the mode-1 mean (one GEMM).
+ * gates_out:   [n_img*B, n_layers*4] fp32 = softmax(leaky_relu(logits)) per group of 4 (saved for bwd).
+ * kv_out: [n_layers, 2, B, P*hid] with P = 4*n_img: for layer l the flat [P, hid] matrices whose
+ * plain reshape(bsz, nh, -1, d) (NOT a head transpose, bert_model.py:585) is the prefix K (slot 0) / V
+ * (slot 1): kv_out[l,s,b,(j*4+r)*hid + c] = sum_i gate[l,(j,b),i] * guids[j,b,r,i*2*hid + s*hid + c]. */
+int mtvaf_gate_fwd(const void* guids, const float* gate_logits, int n_layers, int n_img, int B, int hid,
+                   void* kv_out, float* gates_out, int dtype, void* stream);
+/* d_kv: [n_layers, 2, B, P*hid] fp32.  d_guids (fp32 [n_img,B,4,8*hid]) is ACCUMULATED (+=);
+ * d_gates_scratch [n_img*B, n_layers*4] fp32 must be zeroed by the caller; d_gate_logits same shape (written). */
+int mtvaf_gate_bwd(const float* d_kv, const void* guids, const float* gate_logits, const float* gates, int n_layers,
+                   int n_img, int B, int hid, float* d_guids, float* d_gates_scratch, float* d_gate_logits,
+                   int dtype, void* stream);
+/* 4-way means of the prompt x [rows, 4, W] -> y [rows, W]:
+ *   mode 0: y[row, w]       = mean_r x[row, r, w]                      (guids.mean(dim=1), bert_model.py:550)
+ *   mode 1: y[row, r*S + c] = mean_i x[row, r, i*S + c], S = W/4       (stack(split).sum(0)/4, bert_model.py:567)
+ * backward: dx (fp32 [rows,4,W]) += broadcast(dy) / 4 */
+int mtvaf_mean4_fwd(const void* x, void* y, int64_t rows, int W, int mode, int dtype, void* stream);
+int mtvaf_mean4_bwd_add(const float* dy, float* dx, int64_t rows, int W, int mode, void* stream);
+
+/* ---- ANP heads: softmax + KLDivLoss(batchmean) bert_model.py:553-554,560-561 ------------------ */
+/* logits [rows, ld] fp32, target [B, n] fp32 (row r uses target row r % B); loss_out[head] += ... with
+ * head = r / B; dlogits (optional) = d loss / d logits * scale. */
+int mtvaf_softmax_kl_fwd_bwd(const float* logits, int64_t ld, const float* target, int rows, int B, int n,
+                             float* loss_per_head, float* dlogits, float grad_scale, void* stream);
+
+/* ---- psdProbe: probes/probe.py:74-78, probes/constructLabel.py:11-29, probes/probe_trainModel.py:23-24 */
+/* bit-exact pseudo labels (stable sort + sequential fp32 scan) for norms [B, L] fp32 -> labels [B, L] fp32 */
+int mtvaf_probe_labels(const float* norms, float* labels, int B, int L, void* stream);
+/* loss[0] = mean((norms-labels)^2) ; dnorms (optional) = 2 (norms-labels) / (B L) */
+int mtvaf_mse_fwd_bwd(const float* norms, const float* labels, int64_t n, float* loss, float* dnorms, void* stream);
+/* TwoWordPSDProbe probes/probe.py:25-46: dist[b,i,j] = sum_r (T[b,i,r]-T[b,j,r])^2, explicit differences */
+int mtvaf_pairwise_sqdist(const void* T, int64_t ld, int dtype, int B, int L, int R, float* dist, void* stream);
+
+/* ---- linear-chain CRF (pytorch-crf semantics; call sites bert_model.py:464,511,521) ----------- */
+/* emissions [B, L, T] fp32, tags [B, L] int64, mask [B, L] int64 (mask[:,0] must be 1).
+ * nll_sum[0] += sum_b -(score - logZ); d_emissions (optional) = d(nll_mean)/d emissions;
+ * d_start/d_end/d_trans (optional) accumulated with atomics, all scaled by grad_scale (1/B for mean). */
+int mtvaf_crf_nll_fwd_bwd(const float* emissions, const int64_t* tags, const int64_t* mask, const float* start,
+                          const float* end, const float* trans, int B, int L, int T, float* nll_sum,
+                          float* d_emissions, float* d_start, float* d_end, float* d_trans, float grad_scale,
+                          void* stream);
+/* Viterbi: best_tags [B, L] int64 (positions >= length are -1), lengths [B] int64 */
+int mtvaf_crf_decode(const float* emissions, const int64_t* mask, const float* start, const float* end,
+                     const float* trans, int B, int L, int T, int64_t* best_tags, int64_t* lengths, void* stream);
+
+/* ---- loss combination: probes/loss.py:13-18 + bert_model.py:523-525 without the .item() sync --- */
+/* out[0] = crf_nll_sum/B + (prob_loss > 0.1 ? prob_loss * beta * 2^-epoch : 0) + alpha * img_loss;
+ * flag_out[0] = (prob_loss > 0.1).  All scalars live on the device. */
+int mtvaf_combine_loss(const float* crf_nll_sum, int B, const float* prob_loss, float beta, int epoch,
+                       const float* img_losses, int n_img_losses, float alpha, float* out, int32_t* flag_out,
+                       void* stream);
+
+/* ---- optimizer: torch.optim.AdamW as configured in modules/train.py:887-926 ------------------- */
+int mtvaf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     void* bf16_copy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTVAF_B200_H_ */

@@ -1,0 +1,43 @@
+// Library-level plumbing of the C ABI: last-error string, device properties cache.
+#include "common.cuh"
+#include "../../include/mtvaf_b200.h"
+#include <cstdarg>
+#include <cstring>
+
+namespace mtvaf {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;   // read-only device-properties cache (the only global state of the library)
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace mtvaf
+
+extern "C" int mtvaf_abi_version(void) { return MTVAF_ABI_VERSION; }
+extern "C" const char* mtvaf_last_error(void) { return mtvaf::g_last_error; }
+extern "C" int mtvaf_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  MTVAF_CHECK_CUDA(cudaGetDevice(&dev));
+  int n = 0, ma = 0, mi = 0;
+  MTVAF_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  MTVAF_CHECK_CUDA(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev));
+  MTVAF_CHECK_CUDA(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = n;
+  if (cc_major) *cc_major = ma;
+  if (cc_minor) *cc_minor = mi;
+  return 0;
+}

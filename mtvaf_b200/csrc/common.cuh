@@ -1,0 +1,144 @@
+// Shared device helpers: error handling, bf16 packing, warp/block reductions, counter-based dropout RNG.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace mtvaf {
+
+// ---- error reporting across the C ABI (never throw) -------------------------------------------
+void set_last_error(const char* fmt, ...);
+#define MTVAF_CHECK_CUDA(expr)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::mtvaf::set_last_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,              \
+                              cudaGetErrorName(_e), cudaGetErrorString(_e));              \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+#define MTVAF_REQUIRE(cond, ...)                                                          \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::mtvaf::set_last_error(__VA_ARGS__);                                               \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+#define MTVAF_LAUNCH_CHECK() MTVAF_CHECK_CUDA(cudaGetLastError())
+
+int sm_count();
+
+// ---- element type helpers -----------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// 8-element vector load/store (16 B for bf16, 2x16 B for fp32); pointers must be aligned accordingly
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+// ---- reductions ---------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+// ---- math ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ---- dropout: counter-based hash RNG, recomputed (never stored) in backward ----------------------
+// keep(seed, stream, idx) is a pure function; `stream` separates the dropout sites of one step.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
+  uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
+  uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t h = mix32(lo ^ s0);
+  h = mix32(h + 0x9e3779b9u * (hi + 1u) + s1);
+  return mix32(h ^ (lo * 0x27d4eb2fu));
+}
+// threshold = round(p * 2^32) (clamped); element is KEPT iff bits >= threshold
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
+  return dropout_bits(seed, idx) >= threshold;
+}
+
+}  // namespace mtvaf

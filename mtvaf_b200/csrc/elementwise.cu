@@ -1,0 +1,251 @@
+// Memory-bound helpers: dtype casts, column sums (bias gradients), 4-way means of the visual prompt,
+// MSE (probe loss), loss combination without host sync, fused AdamW.  All are HBM-bound: 16-byte
+// vector loads, grid-stride loops sized to the SM count, warp-shuffle / shared-memory reductions.
+#include "common.cuh"
+#include "../../include/mtvaf_b200.h"
+
+namespace mtvaf {
+
+// ------------------------------------------------------------------ casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  const long long n8 = n / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    Vec8<float>::load(s + i * 8, v);
+    Vec8<__nv_bfloat16>::store(d + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - n8 * 8) d[n8 * 8 + threadIdx.x] = __float2bfloat16_rn(s[n8 * 8 + threadIdx.x]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, long long n) {
+  const long long n8 = n / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    Vec8<__nv_bfloat16>::load(s + i * 8, v);
+    Vec8<float>::store(d + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - n8 * 8) d[n8 * 8 + threadIdx.x] = __bfloat162float(s[n8 * 8 + threadIdx.x]);
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ column sum: db[n] += sum_m dy[m][n]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ dy, long long ld, int M, int N, int rows_per_block,
+                              float* __restrict__ db) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  const int c = blockIdx.x * 64 + tx * 2;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < N) {
+    const bool two = (c + 1 < N);
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const T* p = dy + (long long)r * ld + c;
+      s0 += to_f<T>(p[0]);
+      if (two) s1 += to_f<T>(p[1]);
+    }
+  }
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < N) atomicAdd(db + cc, s);
+  }
+}
+
+// ------------------------------------------------------------------ 4-way means of the prompt
+// x: [rows, 4, W].  mode 0: y[row, w] = mean_r x[row, r, w]                 (bert_model.py:550)
+//                   mode 1: y[row, r*S + c] = mean_i x[row, r, i*S + c], S = W/4   (bert_model.py:567)
+template <typename T>
+__global__ void mean4_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int W, int mode) {
+  const long long total = rows * W;
+  const int S = W / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long row = idx / W;
+    const int w = (int)(idx - row * W);
+    const T* base = x + row * 4 * W;
+    float s;
+    if (mode == 0) {
+      s = to_f<T>(base[w]) + to_f<T>(base[W + w]) + to_f<T>(base[2 * W + w]) + to_f<T>(base[3 * W + w]);
+    } else {
+      const int r = w / S, c = w - r * S;
+      const T* p = base + r * W + c;
+      s = to_f<T>(p[0]) + to_f<T>(p[S]) + to_f<T>(p[2 * S]) + to_f<T>(p[3 * S]);
+    }
+    y[idx] = from_f<T>(s * 0.25f);
+  }
+}
+// dx (fp32, [rows,4,W]) += broadcast(dy)/4
+__global__ void mean4_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long rows, int W,
+                                 int mode) {
+  const long long total = rows * 4 * W;
+  const int S = W / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long row = idx / (4 * W);
+    const int rem = (int)(idx - row * 4 * W);
+    const int r = rem / W, w = rem - r * W;
+    float g;
+    if (mode == 0) g = dy[row * W + w];
+    else g = dy[row * W + r * S + (w % S)];
+    dx[idx] += 0.25f * g;
+  }
+}
+
+// ------------------------------------------------------------------ MSE (probe loss)
+__global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float inv_n,
+                           float* __restrict__ loss, float* __restrict__ da) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = a[i] - b[i];
+    s += d * d;
+    if (da) da[i] = 2.f * d * inv_n;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+}
+
+// ------------------------------------------------------------------ loss combination (device-side predicate)
+__global__ void combine_loss_kernel(const float* crf_nll_sum, float inv_b, const float* prob_loss, float probe_coef,
+                                    const float* img_losses, int n_img, float alpha, float* out, int* flag) {
+  float l = crf_nll_sum[0] * inv_b;
+  int f = 0;
+  if (prob_loss) {
+    const float pl = prob_loss[0];
+    if (pl > 0.1f) { l += pl * probe_coef; f = 1; }     // probes/loss.py:14-16
+  }
+  float img = 0.f;
+  for (int i = 0; i < n_img; ++i) img += img_losses[i];
+  l += alpha * img;                                      // bert_model.py:525
+  out[0] = l;
+  if (flag) flag[0] = f;
+}
+
+// ------------------------------------------------------------------ AdamW (torch.optim.AdamW semantics)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, float gscale, __nv_bfloat16* __restrict__ bf) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float grad = g[i] * gscale;
+    float w = p[i];
+    w *= (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * grad;
+    const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    w -= (lr / bc1) * (mi / denom);
+    p[i] = w;
+    if (bf) bf[i] = __float2bfloat16_rn(w);
+  }
+}
+
+}  // namespace mtvaf
+
+using namespace mtvaf;
+
+extern "C" int mtvaf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  MTVAF_REQUIRE(src && dst, "cast: null pointer");
+  MTVAF_REQUIRE(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0,
+                "cast: pointers must be 16-byte aligned");
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mtvaf_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  MTVAF_REQUIRE(src && dst, "cast: null pointer");
+  MTVAF_REQUIRE(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0,
+                "cast: pointers must be 16-byte aligned");
+  cast_bf16_f32_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, n);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_colsum(const void* dy, int64_t ld, int dtype, int M, int N, float* db, void* stream) {
+  MTVAF_REQUIRE(dy && db && M > 0 && N > 0, "colsum: bad argument");
+  const int col_blocks = (N + 63) / 64;
+  int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+  int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  rows_per_block = ((rows_per_block + 7) / 8) * 8;
+  if (rows_per_block < 8) rows_per_block = 8;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  dim3 grid(col_blocks, row_blocks);
+  if (dtype == MTVAF_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, ld, M, N, rows_per_block, db);
+  else
+    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, ld, M, N, rows_per_block, db);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_mean4_fwd(const void* x, void* y, int64_t rows, int W, int mode, int dtype, void* stream) {
+  MTVAF_REQUIRE(x && y && rows > 0 && W > 0 && W % 4 == 0, "mean4_fwd: bad argument");
+  const int g = grid_for(rows * W, 256);
+  if (dtype == MTVAF_BF16)
+    mean4_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, rows, W, mode);
+  else
+    mean4_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, rows, W, mode);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mtvaf_mean4_bwd_add(const float* dy, float* dx, int64_t rows, int W, int mode, void* stream) {
+  MTVAF_REQUIRE(dy && dx && rows > 0 && W > 0 && W % 4 == 0, "mean4_bwd: bad argument");
+  mean4_bwd_kernel<<<grid_for(rows * 4 * W, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, rows, W, mode);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_mse_fwd_bwd(const float* norms, const float* labels, int64_t n, float* loss, float* dnorms,
+                                 void* stream) {
+  MTVAF_REQUIRE(norms && labels && loss && n > 0, "mse: bad argument");
+  MTVAF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  int g = grid_for(n, 256);
+  if (g > 64) g = 64;
+  mse_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(norms, labels, n, 1.f / (float)n, loss, dnorms);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_combine_loss(const float* crf_nll_sum, int B, const float* prob_loss, float beta, int epoch,
+                                  const float* img_losses, int n_img_losses, float alpha, float* out,
+                                  int32_t* flag_out, void* stream) {
+  MTVAF_REQUIRE(crf_nll_sum && out && B > 0, "combine_loss: bad argument");
+  const float coef = beta * ldexpf(1.f, -epoch);
+  combine_loss_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(crf_nll_sum, 1.f / (float)B, prob_loss, coef, img_losses,
+                                                         img_losses ? n_img_losses : 0, alpha, out, flag_out);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                float grad_scale, void* bf16_copy, void* stream) {
+  if (n <= 0) return 0;
+  MTVAF_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "adamw: bad argument");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                   beta2, eps, weight_decay, bc1, sqrtf(bc2),
+                                                                   grad_scale, (__nv_bfloat16*)bf16_copy);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,149 @@
+// fp32 SIMT GEMM (FFMA) -- the PARITY-mode contraction (fp32 storage and math, so that logits/loss
+// match the fp32 reference to 1e-4 through 12 layers, which tensor-core tf32/bf16 cannot) and the
+// kernel for skinny heads (fc 768->11, projectors 6144->4).  Same operand-major conventions and fused
+// epilogues as the tcgen05 kernel in gemm_tc.cu.
+// 128x128x16 tiles, 256 threads, 8x8 register micro-tile, double-buffered shared memory.
+#include "common.cuh"
+#include "../../include/mtvaf_b200.h"
+#include "epilogue.cuh"
+
+namespace mtvaf {
+
+constexpr int SB_M = 128, SB_N = 128, SB_K = 16, S_THREADS = 256;
+
+// loads a [rows=SB_M or SB_N][SB_K] operand tile into smem laid out [k][row] (row contiguous)
+template <bool MN_MAJOR>
+__device__ __forceinline__ void load_tile(const float* __restrict__ G, long long ld, int row0, int k0, int rows,
+                                          int K, float (*S)[SB_M + 4], bool vec_ok) {
+  const int tid = threadIdx.x;
+  if (!MN_MAJOR) {
+    // G[row][k], k contiguous: 128 rows x 16 k = 512 float4, 2 per thread
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * S_THREADS;
+      const int r = idx >> 2, kq = (idx & 3) * 4;
+      const int gr = row0 + r, gk = k0 + kq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < rows) {
+        const float* p = G + (long long)gr * ld + gk;
+        if (vec_ok && gk + 3 < K) {
+          v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (gk + 0 < K) v.x = p[0];
+          if (gk + 1 < K) v.y = p[1];
+          if (gk + 2 < K) v.z = p[2];
+          if (gk + 3 < K) v.w = p[3];
+        }
+      }
+      S[kq + 0][r] = v.x; S[kq + 1][r] = v.y; S[kq + 2][r] = v.z; S[kq + 3][r] = v.w;
+    }
+  } else {
+    // G[k][row], row contiguous: 16 k x 128 rows = 512 float4, 2 per thread
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * S_THREADS;
+      const int k = idx >> 5, rq = (idx & 31) * 4;
+      const int gk = k0 + k, gr = row0 + rq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < K) {
+        const float* p = G + (long long)gk * ld + gr;
+        if (vec_ok && gr + 3 < rows) {
+          v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (gr + 0 < rows) v.x = p[0];
+          if (gr + 1 < rows) v.y = p[1];
+          if (gr + 2 < rows) v.z = p[2];
+          if (gr + 3 < rows) v.w = p[3];
+        }
+      }
+      *reinterpret_cast<float4*>(&S[k][rq]) = v;
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(S_THREADS)
+gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int M, int N,
+                int K, int k_per_split, EpiArgs ep, int a_vec, int b_vec) {
+  __shared__ __align__(16) float As[2][SB_K][SB_M + 4];
+  __shared__ __align__(16) float Bs[2][SB_K][SB_N + 4];
+  const int m0 = blockIdx.y * SB_M, n0 = blockIdx.x * SB_N;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, each 8x8 outputs
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  int buf = 0;
+  load_tile<A_MN>(A, lda, m0, kbeg, M, kend, As[0], a_vec);
+  load_tile<B_MN>(B, ldb, n0, kbeg, N, kend, Bs[0], b_vec);
+  __syncthreads();
+  for (int k0 = kbeg; k0 < kend; k0 += SB_K) {
+    if (k0 + SB_K < kend) {
+      load_tile<A_MN>(A, lda, m0, k0 + SB_K, M, kend, As[buf ^ 1], a_vec);
+      load_tile<B_MN>(B, ldb, n0, k0 + SB_K, N, kend, Bs[buf ^ 1], b_vec);
+    }
+#pragma unroll
+    for (int k = 0; k < SB_K; ++k) {
+      float a[8], b[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (col < N) epilogue_elem(ep, acc[i][j], row, col, N);
+    }
+  }
+}
+
+}  // namespace mtvaf
+
+using namespace mtvaf;
+
+extern "C" int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                              int b_mn_major, int M, int N, int K, const MtvafEpilogue* epi, int splits,
+                              void* stream) {
+  MTVAF_REQUIRE(A && B && epi, "mtvaf_gemm_f32: null argument");
+  MTVAF_REQUIRE(M > 0 && N > 0 && K > 0, "mtvaf_gemm_f32: empty problem M=%d N=%d K=%d", M, N, K);
+  if (splits < 1) splits = 1;
+  int k_per = ((K + splits - 1) / splits + SB_K - 1) / SB_K * SB_K;
+  splits = (K + k_per - 1) / k_per;
+  EpiArgs ep;
+  int rc = make_epi_args(*epi, MTVAF_F32, M, N, splits, &ep);
+  if (rc) return rc;
+  const float* a = static_cast<const float*>(A);
+  const float* b = static_cast<const float*>(B);
+  const int a_vec = (reinterpret_cast<uintptr_t>(a) % 16 == 0) && (lda % 4 == 0);
+  const int b_vec = (reinterpret_cast<uintptr_t>(b) % 16 == 0) && (ldb % 4 == 0);
+  dim3 grid((N + SB_N - 1) / SB_N, (M + SB_M - 1) / SB_M, splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!a_mn_major && !b_mn_major)
+    gemm_f32_kernel<false, false><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
+  else if (!a_mn_major && b_mn_major)
+    gemm_f32_kernel<false, true><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
+  else if (a_mn_major && b_mn_major)
+    gemm_f32_kernel<true, true><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
+  else
+    gemm_f32_kernel<true, false><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}

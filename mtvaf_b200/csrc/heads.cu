@@ -1,0 +1,448 @@
+// Heads and the small fused ops around the encoder:
+//   * visual-prompt gates + prefix K/V packing   (models/bert_model.py:566-587)
+//   * ANP softmax + KLDivLoss(batchmean)          (models/bert_model.py:553-554,560-561)
+//   * psdProbe pseudo labels, bit-exact           (probes/constructLabel.py:11-29)
+//   * TwoWordPSDProbe pairwise squared distances  (probes/probe.py:25-46)
+//   * linear-chain CRF NLL (+grad) and Viterbi    (pytorch-crf semantics; bert_model.py:511,521)
+#include "common.cuh"
+#include "../../include/mtvaf_b200.h"
+
+namespace mtvaf {
+
+// ================================================================ gates
+// one block per (row = j*B + b, r): S2 = 2*hid columns x 4 splits, all layers
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_fwd_kernel(const T* __restrict__ guids, const float* __restrict__ logits, int n_layers, int n_img, int B, int hid,
+                T* __restrict__ kv_out, float* __restrict__ gates_out) {
+  const int rowr = blockIdx.x;
+  const int row = rowr >> 2, r = rowr & 3;
+  const int j = row / B, b = row - j * B;
+  const int S2 = 2 * hid, W = 4 * S2, P = 4 * n_img;
+  extern __shared__ float sg[];                       // gates [n_layers][4]
+  for (int l = threadIdx.x; l < n_layers; l += blockDim.x) {
+    float v[4], mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x = logits[(long long)row * n_layers * 4 + l * 4 + i];
+      x = x > 0.f ? x : 0.01f * x;                    // F.leaky_relu default slope
+      v[i] = x;
+      mx = fmaxf(mx, x);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float g = v[i] / sum;
+      sg[l * 4 + i] = g;
+      if (r == 0) gates_out[(long long)row * n_layers * 4 + l * 4 + i] = g;
+    }
+  }
+  __syncthreads();
+  const T* src = guids + ((long long)row * 4 + r) * W;
+  const long long kv_stride_l = 2LL * B * P * hid;    // per layer
+  for (int c = threadIdx.x; c < S2; c += blockDim.x) {
+    const float x0 = to_f<T>(src[c]), x1 = to_f<T>(src[S2 + c]), x2 = to_f<T>(src[2 * S2 + c]),
+                x3 = to_f<T>(src[3 * S2 + c]);
+    const int slot = c / hid, cc = c - slot * hid;
+    T* dst = kv_out + ((long long)slot * B + b) * P * hid + (long long)(j * 4 + r) * hid + cc;
+    for (int l = 0; l < n_layers; ++l) {
+      // same accumulation order as the reference loop (:571-572): ((0 + g0 x0) + g1 x1) + ...
+      float acc = 0.f + sg[l * 4 + 0] * x0;
+      acc = acc + sg[l * 4 + 1] * x1;
+      acc = acc + sg[l * 4 + 2] * x2;
+      acc = acc + sg[l * 4 + 3] * x3;
+      dst[l * kv_stride_l] = from_f<T>(acc);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const float* __restrict__ d_kv, const T* __restrict__ guids, const float* __restrict__ gates,
+                int n_layers, int n_img, int B, int hid, float* __restrict__ d_guids, float* __restrict__ d_gates) {
+  __shared__ float red[32];
+  const int rowr = blockIdx.x;
+  const int row = rowr >> 2, r = rowr & 3;
+  const int j = row / B, b = row - j * B;
+  const int S2 = 2 * hid, W = 4 * S2, P = 4 * n_img;
+  const T* src = guids + ((long long)row * 4 + r) * W;
+  float* dsrc = d_guids + ((long long)row * 4 + r) * W;
+  const long long kv_stride_l = 2LL * B * P * hid;
+  for (int l = 0; l < n_layers; ++l) {
+    const float g0 = gates[(long long)row * n_layers * 4 + l * 4 + 0], g1 = gates[(long long)row * n_layers * 4 + l * 4 + 1],
+                g2 = gates[(long long)row * n_layers * 4 + l * 4 + 2], g3 = gates[(long long)row * n_layers * 4 + l * 4 + 3];
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    for (int c = threadIdx.x; c < S2; c += blockDim.x) {
+      const int slot = c / hid, cc = c - slot * hid;
+      const float d = d_kv[l * kv_stride_l + ((long long)slot * B + b) * P * hid + (long long)(j * 4 + r) * hid + cc];
+      p0 += d * to_f<T>(src[c]); p1 += d * to_f<T>(src[S2 + c]);
+      p2 += d * to_f<T>(src[2 * S2 + c]); p3 += d * to_f<T>(src[3 * S2 + c]);
+      dsrc[c] += g0 * d; dsrc[S2 + c] += g1 * d; dsrc[2 * S2 + c] += g2 * d; dsrc[3 * S2 + c] += g3 * d;
+    }
+    p0 = block_sum(p0, red); p1 = block_sum(p1, red); p2 = block_sum(p2, red); p3 = block_sum(p3, red);
+    if (threadIdx.x == 0) {
+      float* dg = d_gates + (long long)row * n_layers * 4 + l * 4;
+      atomicAdd(dg + 0, p0); atomicAdd(dg + 1, p1); atomicAdd(dg + 2, p2); atomicAdd(dg + 3, p3);
+    }
+  }
+}
+
+// softmax + leaky_relu backward on groups of 4
+__global__ void gate_logit_bwd_kernel(const float* __restrict__ d_gates, const float* __restrict__ gates,
+                                      const float* __restrict__ logits, long long n_groups,
+                                      float* __restrict__ d_logits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_groups) return;
+  float g[4], dg[4], dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { g[k] = gates[i * 4 + k]; dg[k] = d_gates[i * 4 + k]; dot += g[k] * dg[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float ds = g[k] * (dg[k] - dot);
+    d_logits[i * 4 + k] = logits[i * 4 + k] > 0.f ? ds : 0.01f * ds;
+  }
+}
+
+// ================================================================ softmax + KL(batchmean)
+__global__ void __launch_bounds__(256)
+softmax_kl_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ target, int B, int n,
+                  float* __restrict__ loss_per_head, float* __restrict__ dlogits, float grad_scale) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int head = row / B, b = row - head * B;
+  const float* x = logits + (long long)row * ld;
+  const float* t = target + (long long)b * n;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, x[i]);
+  mx = block_max(mx, red);
+  float se = 0.f, st = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { se += expf(x[i] - mx); st += t[i]; }
+  se = block_sum(se, red);
+  st = block_sum(st, red);
+  const float lse = mx + logf(se);
+  float loss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float lq = x[i] - lse, ti = t[i];
+    if (ti > 0.f) loss += ti * (logf(ti) - lq);       // xlogy convention: 0 * log 0 = 0
+    if (dlogits) dlogits[(long long)row * ld + i] = (expf(lq) * st - ti) * grad_scale / (float)B;
+  }
+  loss = block_sum(loss, red);
+  if (threadIdx.x == 0) atomicAdd(loss_per_head + head, loss / (float)B);
+}
+
+// ================================================================ probe pseudo labels (bit-exact)
+// one block per sentence: bitonic sort of (value, index) = stable ascending sort, then thread 0 runs the
+// sequential fp32 bucket scan of constructLabel.py:16-25, labels scattered back to original order.
+__global__ void probe_labels_kernel(const float* __restrict__ norms, float* __restrict__ labels, int L, int n_pow2) {
+  extern __shared__ unsigned char smraw[];
+  float* val = reinterpret_cast<float*>(smraw);
+  int* idx = reinterpret_cast<int*>(val + n_pow2);
+  const float* v = norms + (long long)blockIdx.x * L;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    val[i] = i < L ? v[i] : INFINITY;
+    idx[i] = i < L ? i : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int p = i ^ jj;
+        if (p > i) {
+          const bool up = ((i & k) == 0);
+          const float a = val[i], b = val[p];
+          const int ia = idx[i], ib = idx[p];
+          const bool a_gt_b = (a > b) || (a == b && ia > ib);
+          if (a_gt_b == up) { val[i] = b; val[p] = a; idx[i] = ib; idx[p] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    float lab = 0.f;
+    for (int r = 0; r < L; ++r) {
+      if (r == 0) lab = 1.f;
+      else if (r == 1) lab = 2.f;
+      else {
+        const float x = val[r];
+        const float d0 = fabsf(__fsub_rn(x, lab));
+        const float d1 = fabsf(__fsub_rn(__fadd_rn(lab, 1.f), x));
+        if (!(d0 < d1)) lab = __fadd_rn(lab, 1.f);
+      }
+      labels[(long long)blockIdx.x * L + idx[r]] = lab;
+    }
+  }
+}
+
+// ================================================================ TwoWord probe: explicit differences
+template <typename T>
+__global__ void __launch_bounds__(256)
+pairwise_sqdist_kernel(const T* __restrict__ Tm, long long ld, int L, int R, float* __restrict__ dist) {
+  __shared__ float A[16][33], Bt[16][33];
+  const int b = blockIdx.z, i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc = 0.f;
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+      const int rr = e >> 5, cc = e & 31;
+      const int gi = i0 + rr, gj = j0 + rr, gc = r0 + cc;
+      A[rr][cc] = (gi < L && gc < R) ? to_f<T>(Tm[((long long)b * L + gi) * ld + gc]) : 0.f;
+      Bt[rr][cc] = (gj < L && gc < R) ? to_f<T>(Tm[((long long)b * L + gj) * ld + gc]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { const float d = A[ty][c] - Bt[tx][c]; acc = fmaf(d, d, acc); }
+    __syncthreads();
+  }
+  if (i0 + ty < L && j0 + tx < L) dist[((long long)b * L + i0 + ty) * L + j0 + tx] = acc;
+}
+
+// ================================================================ CRF
+// one warp per sequence; lane t < T owns tag t.  Left-aligned masks (length = sum(mask)), mask[:,0] == 1.
+constexpr int CRF_MAX_T = 32;
+
+__device__ __forceinline__ float warp_lse(float v, bool active) {
+  const float x = active ? v : -INFINITY;
+  const float mx = warp_max(x);
+  const float e = active ? __expf(x - mx) : 0.f;
+  return mx + __logf(warp_sum(e));
+}
+
+__global__ void __launch_bounds__(32)
+crf_nll_kernel(const float* __restrict__ em, const long long* __restrict__ tags, const long long* __restrict__ mask,
+               const float* __restrict__ start, const float* __restrict__ end, const float* __restrict__ trans, int L,
+               int T, float* __restrict__ nll_sum, float* __restrict__ d_em, float* __restrict__ d_start,
+               float* __restrict__ d_end, float* __restrict__ d_trans, float gs) {
+  extern __shared__ float alpha[];                 // [L][T]
+  __shared__ float tr[CRF_MAX_T * CRF_MAX_T];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const bool act = t < T;
+  for (int i = t; i < T * T; i += 32) tr[i] = trans[i];
+  int len = 0;
+  for (int i = t; i < L; i += 32) len += (mask[(long long)b * L + i] != 0);
+  len = (int)(warp_sum((float)len) + 0.5f);
+  __syncwarp();
+  const float* e = em + (long long)b * L * T;
+  const long long* tg = tags + (long long)b * L;
+  // forward recursion
+  float a = act ? start[t] + e[t] : -INFINITY;
+  if (act) alpha[t] = a;
+  for (int i = 1; i < len; ++i) {
+    float mx = -INFINITY;
+    float vals[CRF_MAX_T];
+#pragma unroll 1
+    for (int s = 0; s < T; ++s) {
+      const float as = __shfl_sync(0xffffffffu, a, s);
+      const float v = act ? as + tr[s * T + t] : -INFINITY;
+      vals[s] = v;
+      mx = fmaxf(mx, v);
+    }
+    float se = 0.f;
+#pragma unroll 1
+    for (int s = 0; s < T; ++s) se += act ? __expf(vals[s] - mx) : 0.f;
+    a = act ? mx + __logf(se) + e[i * T + t] : -INFINITY;
+    if (act) alpha[i * T + t] = a;
+  }
+  const float logz = warp_lse(a + (act ? end[t] : 0.f), act);
+  // gold path score
+  float score = 0.f;
+  if (t == 0) {
+    int prev = (int)tg[0];
+    score = start[prev] + e[prev];
+    for (int i = 1; i < len; ++i) {
+      const int cur = (int)tg[i];
+      score += tr[prev * T + cur] + e[i * T + cur];
+      prev = cur;
+    }
+    score += end[prev];
+    atomicAdd(nll_sum, logz - score);
+  }
+  if (!d_em) return;
+  __syncwarp();
+  // backward recursion: beta_i[t] = lse_u(trans[t,u] + em_{i+1}[u] + beta_{i+1}[u]); beta_{len-1} = end
+  float beta = act ? end[t] : -INFINITY;
+  for (int i = 0; i < L; ++i)
+    if (act && i >= len) d_em[((long long)b * L + i) * T + t] = 0.f;
+  for (int i = len - 1; i >= 0; --i) {
+    const float al = act ? alpha[i * T + t] : -INFINITY;
+    const float marg = act ? __expf(al + beta - logz) : 0.f;
+    const int gold = (int)tg[i];
+    if (act) d_em[((long long)b * L + i) * T + t] = (marg - (t == gold ? 1.f : 0.f)) * gs;
+    if (i == 0 && act && d_start) atomicAdd(d_start + t, (marg - (t == gold ? 1.f : 0.f)) * gs);
+    if (i == len - 1 && act && d_end) atomicAdd(d_end + t, (marg - (t == gold ? 1.f : 0.f)) * gs);
+    if (i == 0) break;
+    // pairwise marginals for transition (s -> u) at step i: alpha_{i-1}[s] + tr[s,u] + em_i[u] + beta_i[u] - logz
+    const float w = act ? e[i * T + t] + beta : -INFINITY;     // indexed by u = lane
+    const float ap = act ? alpha[(i - 1) * T + t] : -INFINITY; // indexed by s = lane
+    const int gprev = (int)tg[i - 1];
+    float nb_mx = -INFINITY;
+    float vals[CRF_MAX_T];
+#pragma unroll 1
+    for (int u = 0; u < T; ++u) {
+      const float wu = __shfl_sync(0xffffffffu, w, u);
+      const float v = act ? tr[t * T + u] + wu : -INFINITY;    // lane = s
+      vals[u] = v;
+      nb_mx = fmaxf(nb_mx, v);
+      if (act && d_trans) {
+        const float pm = __expf(ap + v - logz);
+        atomicAdd(d_trans + t * T + u, (pm - ((t == gprev && u == gold) ? 1.f : 0.f)) * gs);
+      }
+    }
+    float se = 0.f;
+#pragma unroll 1
+    for (int u = 0; u < T; ++u) se += act ? __expf(vals[u] - nb_mx) : 0.f;
+    beta = act ? nb_mx + __logf(se) : -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+crf_decode_kernel(const float* __restrict__ em, const long long* __restrict__ mask, const float* __restrict__ start,
+                  const float* __restrict__ end, const float* __restrict__ trans, int L, int T,
+                  long long* __restrict__ best, long long* __restrict__ lengths) {
+  extern __shared__ unsigned char hist[];          // [L][T] back-pointers
+  __shared__ float tr[CRF_MAX_T * CRF_MAX_T];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const bool act = t < T;
+  for (int i = t; i < T * T; i += 32) tr[i] = trans[i];
+  int len = 0;
+  for (int i = t; i < L; i += 32) len += (mask[(long long)b * L + i] != 0);
+  len = (int)(warp_sum((float)len) + 0.5f);
+  __syncwarp();
+  const float* e = em + (long long)b * L * T;
+  float sc = act ? start[t] + e[t] : -INFINITY;
+  for (int i = 1; i < len; ++i) {
+    float bestv = -INFINITY;
+    int bests = 0;
+    for (int s = 0; s < T; ++s) {
+      const float ps = __shfl_sync(0xffffffffu, sc, s);
+      const float v = ps + (act ? tr[s * T + t] : 0.f);
+      if (v > bestv) { bestv = v; bests = s; }     // strict >: first maximum wins (torch.max semantics)
+    }
+    if (act) hist[i * T + t] = (unsigned char)bests;
+    sc = act ? bestv + e[i * T + t] : -INFINITY;
+  }
+  sc = act ? sc + end[t] : -INFINITY;
+  // argmax over tags, lowest index on ties
+  float bv = sc;
+  int bi = t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  __syncwarp();
+  if (t == 0) {
+    long long* out = best + (long long)b * L;
+    int cur = bi;
+    for (int i = len - 1; i >= 0; --i) {
+      out[i] = cur;
+      if (i > 0) cur = hist[i * T + cur];
+    }
+    for (int i = len; i < L; ++i) out[i] = -1;
+    lengths[b] = len;
+  }
+}
+
+}  // namespace mtvaf
+
+using namespace mtvaf;
+
+extern "C" int mtvaf_gate_fwd(const void* guids, const float* gate_logits, int n_layers, int n_img, int B, int hid,
+                              void* kv_out, float* gates_out, int dtype, void* stream) {
+  MTVAF_REQUIRE(guids && gate_logits && kv_out && gates_out, "gate_fwd: null argument");
+  MTVAF_REQUIRE(n_layers > 0 && n_img > 0 && B > 0 && hid > 0, "gate_fwd: bad shape");
+  const int blocks = n_img * B * 4;
+  const size_t sm = (size_t)n_layers * 4 * sizeof(float);
+  if (dtype == MTVAF_BF16)
+    gate_fwd_kernel<__nv_bfloat16><<<blocks, 256, sm, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)guids, gate_logits, n_layers, n_img, B, hid, (__nv_bfloat16*)kv_out, gates_out);
+  else
+    gate_fwd_kernel<float><<<blocks, 256, sm, (cudaStream_t)stream>>>((const float*)guids, gate_logits, n_layers,
+                                                                     n_img, B, hid, (float*)kv_out, gates_out);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_gate_bwd(const float* d_kv, const void* guids, const float* gate_logits, const float* gates,
+                              int n_layers, int n_img, int B, int hid, float* d_guids, float* d_gates_scratch,
+                              float* d_gate_logits, int dtype, void* stream) {
+  MTVAF_REQUIRE(d_kv && guids && gate_logits && gates && d_guids && d_gates_scratch && d_gate_logits,
+                "gate_bwd: null argument");
+  const int blocks = n_img * B * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTVAF_BF16)
+    gate_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(d_kv, (const __nv_bfloat16*)guids, gates, n_layers, n_img,
+                                                           B, hid, d_guids, d_gates_scratch);
+  else
+    gate_bwd_kernel<float><<<blocks, 256, 0, st>>>(d_kv, (const float*)guids, gates, n_layers, n_img, B, hid, d_guids,
+                                                   d_gates_scratch);
+  MTVAF_LAUNCH_CHECK();
+  const long long groups = (long long)n_img * B * n_layers;
+  gate_logit_bwd_kernel<<<(int)((groups + 255) / 256), 256, 0, st>>>(d_gates_scratch, gates, gate_logits, groups,
+                                                                     d_gate_logits);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_softmax_kl_fwd_bwd(const float* logits, int64_t ld, const float* target, int rows, int B, int n,
+                                        float* loss_per_head, float* dlogits, float grad_scale, void* stream) {
+  MTVAF_REQUIRE(logits && target && loss_per_head && rows > 0 && B > 0 && n > 0 && rows % B == 0,
+                "softmax_kl: bad argument");
+  softmax_kl_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, target, B, n, loss_per_head, dlogits,
+                                                            grad_scale);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_probe_labels(const float* norms, float* labels, int B, int L, void* stream) {
+  MTVAF_REQUIRE(norms && labels && B > 0 && L > 0, "probe_labels: bad argument");
+  int n2 = 1;
+  while (n2 < L) n2 <<= 1;
+  MTVAF_REQUIRE(n2 <= 4096, "probe_labels: L=%d too long", L);
+  probe_labels_kernel<<<B, n2 < 256 ? (n2 < 32 ? 32 : n2) : 256, (size_t)n2 * 8, (cudaStream_t)stream>>>(norms, labels, L, n2);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_pairwise_sqdist(const void* T, int64_t ld, int dtype, int B, int L, int R, float* dist,
+                                     void* stream) {
+  MTVAF_REQUIRE(T && dist && B > 0 && L > 0 && R > 0, "pairwise_sqdist: bad argument");
+  dim3 grid((L + 15) / 16, (L + 15) / 16, B);
+  if (dtype == MTVAF_BF16)
+    pairwise_sqdist_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)T, ld, L, R, dist);
+  else
+    pairwise_sqdist_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)T, ld, L, R, dist);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_crf_nll_fwd_bwd(const float* emissions, const int64_t* tags, const int64_t* mask,
+                                     const float* start, const float* end, const float* trans, int B, int L, int T,
+                                     float* nll_sum, float* d_emissions, float* d_start, float* d_end, float* d_trans,
+                                     float grad_scale, void* stream) {
+  MTVAF_REQUIRE(emissions && tags && mask && start && end && trans && nll_sum, "crf_nll: null argument");
+  MTVAF_REQUIRE(T > 0 && T <= CRF_MAX_T && B > 0 && L > 0, "crf_nll: bad shape (T <= %d)", CRF_MAX_T);
+  const size_t sm = (size_t)L * T * sizeof(float);
+  MTVAF_REQUIRE(sm <= 40 * 1024, "crf_nll: L*T too large");
+  crf_nll_kernel<<<B, 32, sm, (cudaStream_t)stream>>>(emissions, (const long long*)tags, (const long long*)mask, start,
+                                                      end, trans, L, T, nll_sum, d_emissions, d_start, d_end, d_trans,
+                                                      grad_scale);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_crf_decode(const float* emissions, const int64_t* mask, const float* start, const float* end,
+                                const float* trans, int B, int L, int T, int64_t* best_tags, int64_t* lengths,
+                                void* stream) {
+  MTVAF_REQUIRE(emissions && mask && start && end && trans && best_tags && lengths, "crf_decode: null argument");
+  MTVAF_REQUIRE(T > 0 && T <= CRF_MAX_T && B > 0 && L > 0, "crf_decode: bad shape");
+  const size_t sm = (size_t)L * T;
+  MTVAF_REQUIRE(sm <= 40 * 1024, "crf_decode: L*T too large");
+  crf_decode_kernel<<<B, 32, sm, (cudaStream_t)stream>>>(emissions, (const long long*)mask, start, end, trans, L, T,
+                                                         (long long*)best_tags, (long long*)lengths);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,307 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mtvaf_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic op below is one of the
+library's hand-written sm_100a kernels.  No wrapper has a torch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+F32, BF16 = L.F32, L.BF16
+_raw = L.raw()
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("mtvaf_b200 supports float32 and bfloat16 activations, got %s" % t.dtype)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc: int, name: str):
+    if rc != 0:
+        raise L.MtvafError("%s failed (%d): %s" % (name, rc, L.last_error()))
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.MtvafError("mtvaf_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, M: int, N: int, K: int,
+         mode: int = L.EPI_STORE, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+         bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+         out2: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         p_drop: float = 0.0, seed: int = 0, splits: int = 1, ldo: Optional[int] = None) -> Optional[torch.Tensor]:
+    """D[M,N] = epilogue(alpha * A B^T) -- see MtvafEpilogue in the header. a, b are 2-D row-major
+    tensors: a is [M,K] (a_mn=False) or [K,M] (a_mn=True); same for b with N."""
+    _cuda(a, b, out, bias, aux, out2, rowvec)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    assert a.dtype == b.dtype
+    if out is None and mode != L.EPI_SQNORM:
+        od = out_dtype or (torch.float32 if mode == L.EPI_ATOMIC_F32 else a.dtype)
+        out = torch.empty((M, N), dtype=od, device=a.device)
+    ep = L.Epilogue()
+    ep.mode = mode
+    ep.out_dtype = dt(out) if out is not None else F32
+    ep.out = _p(out)
+    ep.ldo = (ldo if ldo is not None else out.stride(0)) if out is not None else 0
+    ep.bias = _p(bias)
+    ep.aux = _p(aux)
+    ep.ld_aux = aux.stride(0) if aux is not None else 0
+    ep.out2 = _p(out2)
+    ep.ld_out2 = out2.stride(0) if out2 is not None else 0
+    ep.rowvec = _p(rowvec)
+    ep.alpha = alpha
+    ep.p_drop = p_drop
+    ep.seed = seed
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    if aux is not None:
+        assert aux.dtype == a.dtype
+    fn = _raw.mtvaf_gemm_bf16 if a.dtype == torch.bfloat16 else _raw.mtvaf_gemm_f32
+    rc = fn(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), M, N, K, C.byref(ep),
+            splits, _stream())
+    _check(rc, "mtvaf_gemm")
+    return out
+
+
+def linear_fwd(x, w, bias=None, **kw):
+    """y = x w^T + b  (x [M,K], w [N,K])"""
+    return gemm(x, w, M=x.shape[0], N=w.shape[0], K=x.shape[1], bias=bias, **kw)
+
+
+def linear_dgrad(dy, w, **kw):
+    """dx = dy w  (dy [M,N], w [N,K])"""
+    return gemm(dy, w, b_mn=True, M=dy.shape[0], N=w.shape[1], K=dy.shape[1], **kw)
+
+
+def wgrad_splits(m_out: int, n_out: int, k: int, bf16: bool) -> int:
+    bm, bn = (128, 256 if n_out > 128 else 128) if bf16 else (128, 128)
+    tiles = ((m_out + bm - 1) // bm) * ((n_out + bn - 1) // bn)
+    kb = max(1, k // (64 if bf16 else 16))
+    target = 148 * (1 if bf16 else 2)
+    s = max(1, min(kb, (target + tiles - 1) // tiles))
+    return s
+
+
+def linear_wgrad(dy, x, dw: torch.Tensor, *, n_valid: Optional[int] = None):
+    """dw[N,K] += dy^T x  (dy [M,N], x [M,K]); fp32 atomics into the gradient buffer."""
+    M = dy.shape[0]
+    N = n_valid if n_valid is not None else dy.shape[1]
+    K = x.shape[1]
+    gemm(dy, x, a_mn=True, b_mn=True, M=N, N=K, K=M, mode=L.EPI_ATOMIC_F32, out=dw,
+         splits=wgrad_splits(N, K, M, dy.dtype == torch.bfloat16))
+
+
+def colsum(dy: torch.Tensor, db: torch.Tensor, n_valid: Optional[int] = None):
+    _cuda(dy, db)
+    N = n_valid if n_valid is not None else dy.shape[1]
+    _check(_raw.mtvaf_colsum(dy.data_ptr(), dy.stride(0), dt(dy), dy.shape[0], N, db.data_ptr(), _stream()), "colsum")
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _check(_raw.mtvaf_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast")
+    return dst
+
+
+def cast_f32(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(src)
+    assert src.dtype == torch.bfloat16 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    _check(_raw.mtvaf_cast_bf16_to_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------ LN / embeddings
+def layernorm_fwd(z, gamma, beta, eps, y=None):
+    _cuda(z, gamma, beta)
+    rows, H = z.shape
+    if y is None:
+        y = torch.empty_like(z)
+    mean = torch.empty(rows, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=z.device)
+    _check(_raw.mtvaf_layernorm_fwd(z.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, rows, H,
+                                    dt(z), mean.data_ptr(), rstd.data_ptr(), _stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, z, gamma, mean, rstd, d_gamma, d_beta, dz=None):
+    rows, H = z.shape
+    if dz is None:
+        dz = torch.empty_like(z)
+    _check(_raw.mtvaf_layernorm_bwd(dy.data_ptr(), z.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    rows, H, dt(z), dz.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), _stream()),
+           "layernorm_bwd")
+    return dz
+
+
+def embed_ln_fwd(ids, tts, word, pos, typ, gamma, beta, eps, kind, pad_idx, out_dtype, p_drop=0.0, seed=0):
+    _cuda(ids, tts, word)
+    B, Lq = ids.shape
+    H = word.shape[1]
+    out = torch.empty((B * Lq, H), dtype=out_dtype, device=ids.device)
+    pids = torch.empty((B, Lq), dtype=torch.int64, device=ids.device)
+    mean = torch.empty(B * Lq, dtype=torch.float32, device=ids.device)
+    rstd = torch.empty(B * Lq, dtype=torch.float32, device=ids.device)
+    _check(_raw.mtvaf_embed_ln_fwd(ids.data_ptr(), tts.data_ptr(), word.data_ptr(), pos.data_ptr(), typ.data_ptr(),
+                                   gamma.data_ptr(), beta.data_ptr(), eps, kind, pad_idx, B, Lq, H, word.shape[0],
+                                   pos.shape[0], typ.shape[0], out.data_ptr(), dt(out), pids.data_ptr(),
+                                   mean.data_ptr(), rstd.data_ptr(), p_drop, seed, _stream()), "embed_ln_fwd")
+    return out, pids, mean, rstd
+
+
+def embed_ln_bwd(dout, ids, tts, pids, word, pos, typ, gamma, mean, rstd, kind, pad_idx, d_word, d_pos, d_type,
+                 d_gamma, d_beta, p_drop=0.0, seed=0):
+    B, Lq = ids.shape
+    H = word.shape[1]
+    _check(_raw.mtvaf_embed_ln_bwd(dout.data_ptr(), dt(dout), ids.data_ptr(), tts.data_ptr(), pids.data_ptr(),
+                                   word.data_ptr(), pos.data_ptr(), typ.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                   rstd.data_ptr(), kind, pad_idx, B, Lq, H, d_word.data_ptr(), d_pos.data_ptr(),
+                                   d_type.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), p_drop, seed, _stream()),
+           "embed_ln_bwd")
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attention_fwd(qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.0, seed=0, want_probs=False):
+    _cuda(qkv, key_mask)
+    P = 0 if kp is None else kp.shape[2]
+    ctx = torch.empty((B * Lq, nh * d), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B, nh, Lq), dtype=torch.float32, device=qkv.device)
+    probs = torch.empty((B, nh, Lq, P + Lq), dtype=torch.float32, device=qkv.device) if want_probs else None
+    _check(_raw.mtvaf_attention_fwd(qkv.data_ptr(), qkv.stride(0), _p(kp), _p(vp), P, key_mask.data_ptr(), B, Lq, nh,
+                                    d, ctx.data_ptr(), ctx.stride(0), lse.data_ptr(), _p(probs), dt(qkv), p_drop,
+                                    seed, _stream()), "attention_fwd")
+    return ctx, lse, probs
+
+
+def attention_bwd(dctx, qkv, kp, vp, key_mask, ctx, lse, B, Lq, nh, d, dkp=None, dvp=None, p_drop=0.0, seed=0,
+                  dqkv=None):
+    P = 0 if kp is None else kp.shape[2]
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    scratch = torch.empty((B, nh, Lq), dtype=torch.float32, device=qkv.device)
+    _check(_raw.mtvaf_attention_bwd(dctx.data_ptr(), dctx.stride(0), qkv.data_ptr(), qkv.stride(0), _p(kp), _p(vp), P,
+                                    key_mask.data_ptr(), ctx.data_ptr(), ctx.stride(0), lse.data_ptr(), B, Lq, nh, d,
+                                    dqkv.data_ptr(), dqkv.stride(0), _p(dkp), _p(dvp), scratch.data_ptr(), dt(qkv),
+                                    p_drop, seed, _stream()), "attention_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------ fusion / heads
+def mean4_fwd(x, rows, W, mode):
+    y = torch.empty((rows, W), dtype=x.dtype, device=x.device)
+    _check(_raw.mtvaf_mean4_fwd(x.data_ptr(), y.data_ptr(), rows, W, mode, dt(x), _stream()), "mean4_fwd")
+    return y
+
+
+def mean4_bwd_add(dy, dx, rows, W, mode):
+    assert dy.dtype == torch.float32 and dx.dtype == torch.float32
+    _check(_raw.mtvaf_mean4_bwd_add(dy.data_ptr(), dx.data_ptr(), rows, W, mode, _stream()), "mean4_bwd")
+
+
+def gate_fwd(guids, gate_logits, n_layers, n_img, B, hid):
+    P = 4 * n_img
+    kv = torch.empty((n_layers, 2, B, P * hid), dtype=guids.dtype, device=guids.device)
+    gates = torch.empty((n_img * B, n_layers * 4), dtype=torch.float32, device=guids.device)
+    _check(_raw.mtvaf_gate_fwd(guids.data_ptr(), gate_logits.data_ptr(), n_layers, n_img, B, hid, kv.data_ptr(),
+                               gates.data_ptr(), dt(guids), _stream()), "gate_fwd")
+    return kv, gates
+
+
+def gate_bwd(d_kv, guids, gate_logits, gates, n_layers, n_img, B, hid, d_guids):
+    scratch = torch.zeros_like(gates)
+    d_logits = torch.empty_like(gates)
+    _check(_raw.mtvaf_gate_bwd(d_kv.data_ptr(), guids.data_ptr(), gate_logits.data_ptr(), gates.data_ptr(), n_layers,
+                               n_img, B, hid, d_guids.data_ptr(), scratch.data_ptr(), d_logits.data_ptr(), dt(guids),
+                               _stream()), "gate_bwd")
+    return d_logits
+
+
+def softmax_kl(logits, n, target, B, want_grad, grad_scale=1.0):
+    rows = logits.shape[0]
+    loss = torch.zeros(rows // B, dtype=torch.float32, device=logits.device)
+    dlogits = torch.zeros_like(logits) if want_grad else None
+    _check(_raw.mtvaf_softmax_kl_fwd_bwd(logits.data_ptr(), logits.stride(0), target.data_ptr(), rows, B, n,
+                                         loss.data_ptr(), _p(dlogits), grad_scale, _stream()), "softmax_kl")
+    return loss, dlogits
+
+
+def probe_labels(norms):
+    B, Lq = norms.shape
+    labels = torch.empty_like(norms)
+    _check(_raw.mtvaf_probe_labels(norms.data_ptr(), labels.data_ptr(), B, Lq, _stream()), "probe_labels")
+    return labels
+
+
+def mse(norms, labels, want_grad):
+    loss = torch.empty(1, dtype=torch.float32, device=norms.device)
+    dn = torch.empty_like(norms) if want_grad else None
+    _check(_raw.mtvaf_mse_fwd_bwd(norms.data_ptr(), labels.data_ptr(), norms.numel(), loss.data_ptr(), _p(dn),
+                                  _stream()), "mse")
+    return loss, dn
+
+
+def pairwise_sqdist(T, B, Lq, R):
+    dist = torch.empty((B, Lq, Lq), dtype=torch.float32, device=T.device)
+    _check(_raw.mtvaf_pairwise_sqdist(T.data_ptr(), T.stride(0), dt(T), B, Lq, R, dist.data_ptr(), _stream()),
+           "pairwise_sqdist")
+    return dist
+
+
+def crf_nll(em, tags, mask, start, end, trans, want_grad, grad_scale):
+    B, Lq, T = em.shape
+    nll = torch.zeros(1, dtype=torch.float32, device=em.device)
+    if want_grad:
+        d_em = torch.empty_like(em)
+        d_s, d_e, d_t = torch.zeros_like(start), torch.zeros_like(end), torch.zeros_like(trans)
+    else:
+        d_em = d_s = d_e = d_t = None
+    _check(_raw.mtvaf_crf_nll_fwd_bwd(em.data_ptr(), tags.data_ptr(), mask.data_ptr(), start.data_ptr(),
+                                      end.data_ptr(), trans.data_ptr(), B, Lq, T, nll.data_ptr(), _p(d_em), _p(d_s),
+                                      _p(d_e), _p(d_t), grad_scale, _stream()), "crf_nll")
+    return nll, d_em, d_s, d_e, d_t
+
+
+def crf_decode(em, mask, start, end, trans):
+    B, Lq, T = em.shape
+    best = torch.empty((B, Lq), dtype=torch.int64, device=em.device)
+    lens = torch.empty(B, dtype=torch.int64, device=em.device)
+    _check(_raw.mtvaf_crf_decode(em.data_ptr(), mask.data_ptr(), start.data_ptr(), end.data_ptr(), trans.data_ptr(),
+                                 B, Lq, T, best.data_ptr(), lens.data_ptr(), _stream()), "crf_decode")
+    return best, lens
+
+
+def combine_loss(crf_nll_sum, B, prob_loss, beta, epoch, img_losses, alpha):
+    out = torch.empty(1, dtype=torch.float32, device=crf_nll_sum.device)
+    flag = torch.empty(1, dtype=torch.int32, device=crf_nll_sum.device)
+    n_img = 0 if img_losses is None else img_losses.numel()
+    _check(_raw.mtvaf_combine_loss(crf_nll_sum.data_ptr(), B, _p(prob_loss), beta, epoch, _p(img_losses), n_img,
+                                   alpha, out.data_ptr(), flag.data_ptr(), _stream()), "combine_loss")
+    return out, flag
+
+
+def adamw_step(param, grad, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0, bf16_copy=None):
+    _check(_raw.mtvaf_adamw_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), lr, b1,
+                                 b2, eps, wd, step, grad_scale, _p(bf16_copy), _stream()), "adamw_step")

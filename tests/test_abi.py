@@ -1,0 +1,48 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/mtvaf_b200.h declares
+(no compute calls without a GPU)."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "mtvaf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtvaf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mtvaf_b200 import build
+    build.build()
+    from mtvaf_b200 import lib
+    names = header_functions()
+    assert len(names) >= 20
+    raw = lib.raw()
+    for n in names:
+        assert hasattr(raw, n), "symbol %s declared in the header but not exported" % n
+    # and the ctypes table binds every one of them
+    for n in names:
+        if n != "mtvaf_last_error":
+            assert n in lib.SIGNATURES, n
+    assert lib.abi_version() == 1
+
+
+def test_no_cpu_fallback_in_product_package():
+    """The product package must never import the oracle."""
+    pkg = os.path.join(ROOT, "mtvaf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                s = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in s and "from oracle" not in s, os.path.join(dirpath, f)
+
+
+def test_bad_arguments_return_error_not_crash():
+    import ctypes as C
+    from mtvaf_b200 import lib
+    ep = lib.Epilogue()
+    rc = lib.raw().mtvaf_gemm_bf16(None, 0, 0, None, 0, 0, 0, 0, 0, C.byref(ep), 1, None)
+    assert rc == -1 and "null" in lib.last_error()
+    rc = lib.raw().mtvaf_probe_labels(None, None, 0, 0, None)
+    assert rc == -1

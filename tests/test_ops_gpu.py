@@ -1,0 +1,417 @@
+"""GPU parity of every C-ABI kernel against the oracle / plain torch fp32 on the same seeded inputs.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mtvaf_oracle as O   # checker only
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mtvaf_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def Lb():
+    from mtvaf_b200 import lib
+    return lib
+
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+# ---------------------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [(128, 256, 64), (256, 768, 768), (384, 2304, 768), (200, 800, 3840), (64, 6144, 800),
+               (130, 48, 6144), (512, 384, 768), (96, 2089, 6144), (2048, 768, 3072)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_forward_layout(ops, Lb, dtype, M, N, K):
+    x = rnd(M, K, seed=1, dtype=dtype)
+    w = rnd(N, K, seed=2, scale=0.05, dtype=dtype)
+    bias = rnd(N, seed=3)
+    y = ops.linear_fwd(x, w, bias)
+    ref = x.float() @ w.float().t() + bias
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-5
+    assert rel_err(y, ref) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (200, 768, 3072), (384, 3072, 768), (64, 3840, 800), (96, 6144, 2089)])
+def test_gemm_dgrad_layout(ops, Lb, dtype, M, N, K):
+    # dX[M,N] = dY[M,K] W[K,N]   (B operand MN-major)
+    ld = (K + 7) // 8 * 8
+    dy_full = torch.zeros(M, ld, dtype=dtype, device=DEV)
+    dy_full[:, :K] = rnd(M, K, seed=4, dtype=dtype)
+    dy = dy_full[:, :K]
+    w = rnd(K, N, seed=5, scale=0.05, dtype=dtype)
+    out = ops.gemm(dy, w, b_mn=True, M=M, N=N, K=K)
+    ref = dy.float() @ w.float()
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-5
+    assert rel_err(out, ref) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("T,N,K", [(256, 768, 768), (1000, 3072, 768), (4096, 768, 3072), (64, 800, 3840), (96, 48, 6144)])
+def test_gemm_wgrad_layout(ops, Lb, dtype, T, N, K):
+    # dW[N,K] += dY[T,N]^T X[T,K]  (both MN-major, split-K fp32 atomics)
+    dy = rnd(T, N, seed=6, dtype=dtype)
+    x = rnd(T, K, seed=7, dtype=dtype)
+    dw = torch.zeros(N, K, dtype=torch.float32, device=DEV)
+    ops.linear_wgrad(dy, x, dw)
+    ref = dy.float().t() @ x.float()
+    tol = 1e-2 if dtype == torch.bfloat16 else 5e-5
+    assert rel_err(dw, ref) < tol
+    ops.linear_wgrad(dy, x, dw)       # accumulates
+    assert rel_err(dw, 2 * ref) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_epilogues(ops, Lb, dtype):
+    M, N, K = 300, 768, 256
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 3e-5
+    x = rnd(M, K, seed=1, dtype=dtype)
+    w = rnd(N, K, seed=2, scale=0.08, dtype=dtype)
+    bias = rnd(N, seed=3)
+    base = x.float() @ w.float().t() + bias
+    # GELU with pre-activation side output
+    pre = torch.empty(M, N, dtype=dtype, device=DEV)
+    g = ops.linear_fwd(x, w, bias, mode=Lb.EPI_GELU, out2=pre)
+    assert rel_err(pre, base) < tol
+    assert rel_err(g, F.gelu(base)) < tol
+    # tanh
+    t = ops.linear_fwd(x, w, bias, mode=Lb.EPI_TANH)
+    assert rel_err(t, torch.tanh(base)) < tol
+    # residual (no dropout)
+    res = rnd(M, N, seed=9, dtype=dtype)
+    r = ops.linear_fwd(x, w, bias, mode=Lb.EPI_RESID, aux=res)
+    assert rel_err(r, base + res.float()) < tol
+    # residual with dropout: kept fraction and scaling
+    r2 = ops.linear_fwd(x, w, bias, mode=Lb.EPI_RESID, aux=torch.zeros_like(res), p_drop=0.25, seed=1234)
+    kept = (r2.float() != 0).float().mean().item()
+    assert abs(kept - 0.75) < 0.01
+    mask = r2.float() != 0
+    assert rel_err(r2.float()[mask], (base / 0.75)[mask]) < tol
+    r3 = ops.linear_fwd(x, w, bias, mode=Lb.EPI_RESID, aux=torch.zeros_like(res), p_drop=0.25, seed=1234)
+    assert torch.equal(r2, r3)                      # counter-based: reproducible
+    # dgelu multiply
+    pre_in = rnd(M, N, seed=11, dtype=dtype)
+    dg = ops.linear_fwd(x, w, None, mode=Lb.EPI_MUL_DGELU, aux=pre_in)
+    pf = pre_in.float().requires_grad_()
+    F.gelu(pf).sum().backward()
+    assert rel_err(dg, (base - bias) * pf.grad) < tol
+    # dtanh multiply
+    th = torch.tanh(rnd(M, N, seed=12)).to(dtype)
+    dth = ops.linear_fwd(x, w, None, mode=Lb.EPI_MUL_DTANH, aux=th)
+    assert rel_err(dth, (base - bias) * (1 - th.float() ** 2)) < tol
+    # squared norm rows (+ optional store)
+    rowsq = torch.zeros(M, dtype=torch.float32, device=DEV)
+    tt = ops.linear_fwd(x, w, None, mode=Lb.EPI_SQNORM, rowvec=rowsq, out=torch.empty(M, N, dtype=dtype, device=DEV))
+    assert rel_err(rowsq, ((base - bias) ** 2).sum(1)) < tol
+    assert rel_err(tt, base - bias) < tol
+    # row scale, fp32 output
+    rs = rnd(M, seed=13)
+    o = ops.linear_fwd(x, w, None, mode=Lb.EPI_ROWSCALE, rowvec=rs, out_dtype=torch.float32)
+    assert o.dtype == torch.float32
+    assert rel_err(o, (base - bias) * rs[:, None]) < tol
+
+
+def test_gemm_bf16_large_persistent(ops, Lb):
+    """More tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and phases."""
+    M, N, K = 8192, 2304, 768
+    x = rnd(M, K, seed=21, dtype=torch.bfloat16)
+    w = rnd(N, K, seed=22, scale=0.05, dtype=torch.bfloat16)
+    y = ops.linear_fwd(x, w, None)
+    ref = (x.float() @ w.float().t())
+    assert rel_err(y, ref) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------- LN / embeddings
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H", [768, 1024])
+def test_layernorm_fwd_bwd(ops, dtype, H):
+    rows = 777
+    z = rnd(rows, H, seed=1, dtype=dtype)
+    gamma, beta = 1 + 0.1 * rnd(H, seed=2), 0.1 * rnd(H, seed=3)
+    y, mean, rstd = ops.layernorm_fwd(z, gamma, beta, 1e-5)
+    zf = z.float().requires_grad_()
+    gf, bf_ = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    ref = F.layer_norm(zf, (H,), gf, bf_, 1e-5)
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert rel_err(y, ref) < tol
+    dy = rnd(rows, H, seed=4, dtype=dtype)
+    ref.backward(dy.float())
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dz = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg, db)
+    assert rel_err(dz, zf.grad) < tol
+    assert rel_err(dg, gf.grad) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    assert rel_err(db, bf_.grad) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["roberta", "bert"])
+def test_embed_ln_fwd_bwd(ops, kind):
+    cfg = O.EncoderCfg.roberta_base(vocab_size=500) if kind == "roberta" else O.EncoderCfg.bert_base(vocab_size=500)
+    H = cfg.hidden_size
+    g = torch.Generator().manual_seed(5)
+    B, Lq = 5, 37
+    ids = torch.randint(0, 500, (B, Lq), generator=g)
+    ids[:, 25:] = 0
+    ids[1, 3] = 1
+    ids[2, :4] = 1
+    tts = torch.randint(0, cfg.type_vocab_size, (B, Lq), generator=g)
+    p = {"bert.embeddings.word_embeddings.weight": torch.randn(500, H, generator=g) * 0.05,
+         "bert.embeddings.position_embeddings.weight": torch.randn(cfg.max_position_embeddings, H, generator=g) * 0.05,
+         "bert.embeddings.token_type_embeddings.weight": torch.randn(cfg.type_vocab_size, H, generator=g) * 0.05,
+         "bert.embeddings.LayerNorm.weight": 1 + 0.1 * torch.randn(H, generator=g),
+         "bert.embeddings.LayerNorm.bias": 0.1 * torch.randn(H, generator=g)}
+    p = {k: v.requires_grad_() for k, v in p.items()}
+    ref, ref_pos = O.embeddings(p, cfg, ids, tts)
+    dout = torch.randn(B, Lq, H, generator=g)
+    ref.backward(dout)
+    d = {k: v.detach().to(DEV) for k, v in p.items()}
+    kid = 0 if kind == "roberta" else 1
+    out, pids, mean, rstd = ops.embed_ln_fwd(ids.to(DEV), tts.to(DEV), d["bert.embeddings.word_embeddings.weight"],
+                                             d["bert.embeddings.position_embeddings.weight"],
+                                             d["bert.embeddings.token_type_embeddings.weight"],
+                                             d["bert.embeddings.LayerNorm.weight"], d["bert.embeddings.LayerNorm.bias"],
+                                             cfg.layer_norm_eps, kid, cfg.pad_token_id, torch.float32)
+    assert torch.equal(pids.cpu(), ref_pos)          # bit-exact int64
+    assert rel_err(out.view(B, Lq, H), ref) < 1e-5
+    grads = [torch.zeros_like(d[k]) for k in ("bert.embeddings.word_embeddings.weight",
+                                              "bert.embeddings.position_embeddings.weight",
+                                              "bert.embeddings.token_type_embeddings.weight",
+                                              "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias")]
+    ops.embed_ln_bwd(dout.to(DEV).view(B * Lq, H), ids.to(DEV), tts.to(DEV), pids,
+                     d["bert.embeddings.word_embeddings.weight"], d["bert.embeddings.position_embeddings.weight"],
+                     d["bert.embeddings.token_type_embeddings.weight"], d["bert.embeddings.LayerNorm.weight"], mean,
+                     rstd, kid, cfg.pad_token_id, *grads)
+    for gr, k in zip(grads, ("bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+                             "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.LayerNorm.weight",
+                             "bert.embeddings.LayerNorm.bias")):
+        assert rel_err(gr, p[k].grad) < 1e-4, k
+
+
+# ---------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, kp, vp, mask, B, Lq, nh, d):
+    H = nh * d
+    q, k, v = qkv.view(B, Lq, 3, nh, d).permute(2, 0, 3, 1, 4)
+    if kp is not None:
+        k = torch.cat([kp, k], 2)
+        v = torch.cat([vp, v], 2)
+        full = torch.cat([torch.ones(B, kp.shape[2]), mask.float()], 1)
+    else:
+        full = mask.float()
+    s = q @ k.transpose(-1, -2) / math.sqrt(d) + O.extended_mask(full)
+    pr = torch.softmax(s, -1)
+    return (pr @ v).permute(0, 2, 1, 3).reshape(B * Lq, H), pr
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Lq,P", [(2, 128, 16), (3, 40, 36), (2, 77, 0), (1, 200, 100)])
+def test_attention_fwd_bwd(ops, dtype, B, Lq, P):
+    nh, d = 12, 64
+    g = torch.Generator().manual_seed(B * 1000 + Lq)
+    qkv = (torch.randn(B * Lq, 3 * nh * d, generator=g)).to(dtype).float().requires_grad_()
+    kp = vp = None
+    if P:
+        kp = torch.randn(B, nh, P, d, generator=g).to(dtype).float().requires_grad_()
+        vp = torch.randn(B, nh, P, d, generator=g).to(dtype).float().requires_grad_()
+    lens = torch.randint(5, Lq + 1, (B,), generator=g)
+    mask = (torch.arange(Lq)[None] < lens[:, None]).long()
+    ref, ref_pr = _attn_ref(qkv, kp, vp, mask, B, Lq, nh, d)
+    dctx = torch.randn(B * Lq, nh * d, generator=g).to(dtype).float()
+    ref.backward(dctx)
+    to = lambda t: None if t is None else t.detach().to(dtype).to(DEV)
+    ctx, lse, probs = ops.attention_fwd(to(qkv), to(kp), to(vp), mask.to(DEV), B, Lq, nh, d, want_probs=True)
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
+    assert rel_err(ctx, ref) < tol
+    assert rel_err(probs, ref_pr) < (1e-2 if dtype == torch.bfloat16 else 2e-5)
+    dkp = torch.zeros(B, nh, P, d, device=DEV) if P else None
+    dvp = torch.zeros(B, nh, P, d, device=DEV) if P else None
+    dqkv = ops.attention_bwd(to(dctx), to(qkv), to(kp), to(vp), mask.to(DEV), ctx, lse, B, Lq, nh, d, dkp, dvp)
+    btol = 3e-2 if dtype == torch.bfloat16 else 5e-5
+    assert rel_err(dqkv, qkv.grad) < btol
+    if P:
+        assert rel_err(dkp, kp.grad) < btol
+        assert rel_err(dvp, vp.grad) < btol
+
+
+def test_attention_dropout_consistency(ops):
+    """fwd/bwd regenerate the same mask: finite-difference-free check via linearity in V."""
+    B, Lq, P, nh, d = 2, 64, 16, 12, 64
+    qkv = rnd(B * Lq, 3 * nh * d, seed=1)
+    kp, vp = rnd(B, nh, P, d, seed=2), rnd(B, nh, P, d, seed=3)
+    mask = torch.ones(B, Lq, dtype=torch.long, device=DEV)
+    ctx, lse, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=0.1, seed=77)
+    ctx2, _, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=0.1, seed=77)
+    assert torch.equal(ctx, ctx2)
+    # ctx is linear in V for fixed probabilities+mask: <dctx, ctx(V)> gradient wrt vp must equal dvp
+    dctx = rnd(B * Lq, nh * d, seed=4)
+    dkp, dvp = torch.zeros_like(kp), torch.zeros_like(vp)
+    ops.attention_bwd(dctx, qkv, kp, vp, mask, ctx, lse, B, Lq, nh, d, dkp, dvp, p_drop=0.1, seed=77)
+    e = torch.zeros_like(vp)
+    e[1, 3, 5, 7] = 1.0
+    ctx_e, _, _ = ops.attention_fwd(qkv, kp, vp + e, mask, B, Lq, nh, d, p_drop=0.1, seed=77)
+    fd = ((ctx_e - ctx) * dctx).sum()
+    assert abs(float(fd) - float(dvp[1, 3, 5, 7])) < 1e-3 * (1 + abs(float(fd)))
+
+
+# ---------------------------------------------------------------------------------------- fusion
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gate_and_mean4(ops, dtype):
+    n_layers, n_img, B, hid = 12, 4, 3, 768
+    W = 8 * hid
+    guids = rnd(n_img, B, 4, W, seed=1, dtype=dtype)
+    gf = guids.float().requires_grad_()
+    # mean4 modes
+    m0 = ops.mean4_fwd(guids, n_img * B, W, 0)
+    assert rel_err(m0, gf.detach().view(n_img * B, 4, W).mean(1)) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+    m1 = ops.mean4_fwd(guids, n_img * B, W, 1)
+    ref1 = torch.stack(gf.detach().view(n_img * B, 4, W).split(2 * hid, -1)).sum(0).view(n_img * B, -1) / 4
+    assert rel_err(m1, ref1) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+    logits = rnd(n_img * B, n_layers * 4, seed=2).requires_grad_()
+    kv, gates = ops.gate_fwd(guids, logits.detach(), n_layers, n_img, B, hid)
+    # reference (bert_model.py:566-587)
+    res = []
+    for l in range(n_layers):
+        kvs = []
+        for j in range(n_img):
+            sp = gf[j].split(2 * hid, -1)
+            gte = torch.softmax(F.leaky_relu(logits[j * B:(j + 1) * B, l * 4:(l + 1) * 4]), -1)
+            kvs.append(sum(gte[:, i].view(-1, 1, 1) * sp[i] for i in range(4)))
+        c = torch.cat(kvs, 1)
+        k, v = c.split(hid, -1)
+        res.append(torch.stack([k.reshape(B, -1), v.reshape(B, -1)]))
+    ref = torch.stack(res)                  # [L,2,B,P*hid]
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert rel_err(kv, ref) < tol
+    dkv = rnd(*ref.shape, seed=3)
+    ref.backward(dkv)
+    d_guids = torch.zeros(n_img, B, 4, W, device=DEV)
+    d_logits = ops.gate_bwd(dkv, guids, logits.detach(), gates, n_layers, n_img, B, hid, d_guids)
+    assert rel_err(d_guids, gf.grad) < tol
+    assert rel_err(d_logits, logits.grad) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    # mean4 backward
+    dx = torch.zeros(n_img * B, 4, W, device=DEV)
+    dy = rnd(n_img * B, W, seed=4)
+    ops.mean4_bwd_add(dy, dx, n_img * B, W, 0)
+    assert rel_err(dx, dy[:, None, :].expand(-1, 4, -1) / 4) < 1e-6
+    dx.zero_()
+    ops.mean4_bwd_add(dy, dx, n_img * B, W, 1)
+    x = torch.zeros(n_img * B, 4, W, device=DEV, requires_grad=True)
+    (torch.stack(x.split(2 * hid, -1)).sum(0).view(n_img * B, -1) / 4 * dy).sum().backward()
+    assert rel_err(dx, x.grad) < 1e-6
+
+
+def test_softmax_kl(ops):
+    B, n, heads = 5, 2089, 4
+    ld = 2096
+    logits_full = torch.zeros(heads * B, ld, device=DEV)
+    logits_full[:, :n] = rnd(heads * B, n, seed=1, scale=2.0)
+    target = torch.softmax(rnd(B, n, seed=2), -1)
+    lg = logits_full[:, :n].clone().requires_grad_()
+    ref = torch.stack([F.kl_div(torch.softmax(lg[h * B:(h + 1) * B], -1).log(), target, reduction="batchmean")
+                       for h in range(heads)])
+    ref.sum().backward()
+    loss, dl = ops.softmax_kl(logits_full, n, target, B, True)
+    assert rel_err(loss, ref) < 1e-5
+    assert rel_err(dl[:, :n], lg.grad) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------- probe
+def test_probe_labels_bit_exact(ops, golden_dir):
+    import os
+    g = torch.load(os.path.join(golden_dir, "probe_kat.pt"), weights_only=False)
+    for key in ("label_kat", "label_big"):
+        out = ops.probe_labels(g[key + "_in"].to(DEV).contiguous())
+        assert torch.equal(out.cpu(), g[key + "_out"])
+    gen = torch.Generator().manual_seed(3)
+    for Lq in (1, 2, 3, 31, 128, 200, 500):
+        v = torch.rand(4, Lq, generator=gen) * 60
+        v[0] = torch.round(v[0])                      # many exact ties
+        assert torch.equal(ops.probe_labels(v.to(DEV)).cpu(), O.construct_label(v))
+
+
+def test_mse_and_pairwise(ops):
+    a, b = rnd(16, 128, seed=1, scale=30), rnd(16, 128, seed=2, scale=30)
+    loss, da = ops.mse(a, b, True)
+    af = a.clone().requires_grad_()
+    ref = F.mse_loss(af, b)
+    ref.backward()
+    assert rel_err(loss, ref.view(1)) < 1e-5
+    assert rel_err(da, af.grad) < 1e-5
+    T = rnd(2 * 50, 384, seed=3)
+    T[7] = T[9]                                        # identical rows -> exactly 0
+    dist = ops.pairwise_sqdist(T, 2, 50, 384)
+    t = T.view(2, 50, 384)
+    ref = ((t.unsqueeze(2) - t.unsqueeze(1)) ** 2).sum(-1)
+    assert rel_err(dist, ref) < 1e-5
+    assert float(dist[0].diagonal().abs().max()) == 0.0 and float(dist[0, 7, 9]) == 0.0
+    assert torch.equal(dist, dist.transpose(1, 2))
+
+
+# ---------------------------------------------------------------------------------------- CRF
+def test_crf(ops):
+    g = torch.Generator().manual_seed(4)
+    B, Lq, T = 9, 40, 11
+    em = torch.randn(B, Lq, T, generator=g).requires_grad_()
+    start = (torch.rand(T, generator=g) * 0.2 - 0.1).requires_grad_()
+    end = (torch.rand(T, generator=g) * 0.2 - 0.1).requires_grad_()
+    trans = (torch.rand(T, T, generator=g) * 2 - 1).requires_grad_()
+    lens = torch.randint(1, Lq + 1, (B,), generator=g)
+    lens[0], lens[1] = 1, Lq
+    mask = (torch.arange(Lq)[None] < lens[:, None]).long()
+    tags = torch.randint(0, T, (B, Lq), generator=g)
+    ref = -O.crf_log_likelihood(em, tags, mask, start, end, trans).mean()
+    ref.backward()
+    c = lambda t: t.detach().to(DEV).contiguous()
+    nll, d_em, d_s, d_e, d_t = ops.crf_nll(c(em), c(tags), c(mask), c(start), c(end), c(trans), True, 1.0 / B)
+    assert rel_err(nll / B, ref.view(1)) < 1e-5
+    assert rel_err(d_em, em.grad) < 1e-4
+    assert rel_err(d_s, start.grad) < 1e-4
+    assert rel_err(d_e, end.grad) < 1e-4
+    assert rel_err(d_t, trans.grad) < 1e-4
+    best, ln = ops.crf_decode(c(em), c(mask), c(start), c(end), c(trans))
+    dec = O.crf_decode(em, mask, start, end, trans)
+    assert ln.cpu().tolist() == lens.tolist()
+    for b in range(B):
+        assert best[b, :lens[b]].cpu().tolist() == dec[b]
+        assert (best[b, lens[b]:] == -1).all()
+
+
+def test_combine_loss_and_adamw(ops):
+    nll = torch.tensor([33.0], device=DEV)
+    pl = torch.tensor([1500.0], device=DEV)
+    img = torch.tensor([0.3, 0.2, 0.1, 0.4], device=DEV)
+    out, flag = ops.combine_loss(nll, 4, pl, 0.5, 30, img, 0.1)
+    ref = 33.0 / 4 + 1500.0 * 0.5 * 2 ** -30 + 0.1 * 1.0
+    assert abs(float(out) - ref) < 1e-5 and int(flag) == 1
+    out, flag = ops.combine_loss(nll, 4, torch.tensor([0.05], device=DEV), 0.5, 30, None, 0.1)
+    assert abs(float(out) - 33.0 / 4) < 1e-6 and int(flag) == 0
+    p = rnd(1000, seed=1).requires_grad_()
+    p2 = p.detach().clone()
+    opt = torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    m, v = torch.zeros_like(p2), torch.zeros_like(p2)
+    for step in range(1, 4):
+        gr = rnd(1000, seed=10 + step)
+        p.grad = gr.clone()
+        opt.step()
+        ops.adamw_step(p2, gr, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+    assert rel_err(p2, p.detach()) < 1e-6
