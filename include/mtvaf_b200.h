@@ -82,6 +82,16 @@ int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, in
 /* ---- elementwise / reductions --------------------------------------------------------------- */
 int mtvaf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int mtvaf_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* y[i] = keep(seed, i) ? x[i] / (1-p) : 0 -- the same counter-based mask the MTVAF_EPI_RESID epilogue uses
+ * with element index i = m * N + n, so backward regenerates forward's mask (nn.Dropout :297,380, bert_model.py:506) */
+int mtvaf_dropout_apply(const void* x, void* y, int64_t n, int dtype, float p_drop, uint64_t seed, void* stream);
+/* dst[i] += alpha * src[i] with independent dtypes (gradient injection at hidden_states[7], residual joins) */
+int mtvaf_add_inplace(void* dst, int dst_dtype, const void* src, int src_dtype, int64_t n, float alpha, void* stream);
+/* y[m,n] = x[m,n] * alpha * rowscale[m]  (probe backward dT = 2 g_m T_m, probes/probe.py:74-78) */
+int mtvaf_rowscale(const void* x, const float* rowscale, void* y, int64_t M, int N, float alpha, int dtype,
+                   void* stream);
+/* x[i] *= scalar[0], scalar on the device: scales head gradients by d(loss) without a host sync */
+int mtvaf_scale_by_device_scalar(float* x, int64_t n, const float* scalar, void* stream);
 /* db[n] += sum_m dY[m,n]   (bias gradients; fp32 atomics into the grad bucket) */
 int mtvaf_colsum(const void* dy, int64_t ld, int dtype, int M, int N, float* db, void* stream);
 

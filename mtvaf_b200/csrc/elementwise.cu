@@ -106,6 +106,38 @@ __global__ void mean4_bwd_kernel(const float* __restrict__ dy, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------ dropout apply / accumulate
+template <typename T>
+__global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, uint32_t thr,
+                                     float scale, unsigned long long seed) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = dropout_keep(seed, (unsigned long long)i, thr) ? from_f<T>(to_f<T>(x[i]) * scale) : from_f<T>(0.f);
+}
+template <typename TD, typename TS>
+__global__ void add_inplace_kernel(TD* __restrict__ dst, const TS* __restrict__ src, long long n, float alpha) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = from_f<TD>(to_f<TD>(dst[i]) + alpha * to_f<TS>(src[i]));
+}
+
+// ------------------------------------------------------------------ row scale / device-scalar scale
+// y[m, n] = x[m, n] * alpha * rowscale[m]   (probe backward: dT = 2 g_m T_m)
+template <typename T>
+__global__ void rowscale_kernel(const T* __restrict__ x, const float* __restrict__ rs, T* __restrict__ y, long long M,
+                                int N, float alpha) {
+  const long long total = M * N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    y[i] = from_f<T>(to_f<T>(x[i]) * alpha * rs[i / N]);
+}
+// x[i] *= s[0] with s on the device (scaling head gradients by d(loss) without a host sync)
+__global__ void scale_dev_kernel(float* __restrict__ x, long long n, const float* __restrict__ s) {
+  const float f = s[0];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= f;
+}
+
 // ------------------------------------------------------------------ MSE (probe loss)
 __global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float inv_n,
                            float* __restrict__ loss, float* __restrict__ da) {
@@ -180,6 +212,41 @@ extern "C" int mtvaf_cast_bf16_to_f32(const void* src, float* dst, int64_t n, vo
   return 0;
 }
 
+extern "C" int mtvaf_dropout_apply(const void* x, void* y, int64_t n, int dtype, float p_drop, uint64_t seed,
+                                   void* stream) {
+  if (n <= 0) return 0;
+  MTVAF_REQUIRE(x && y && p_drop >= 0.f && p_drop < 1.f, "dropout_apply: bad argument");
+  double t = (double)p_drop * 4294967296.0;
+  const uint32_t thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+  const float scale = 1.f / (1.f - p_drop);
+  if (dtype == MTVAF_BF16)
+    dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, thr, scale, seed);
+  else
+    dropout_apply_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, n, thr,
+                                                                                    scale, seed);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_add_inplace(void* dst, int dst_dtype, const void* src, int src_dtype, int64_t n, float alpha,
+                                 void* stream) {
+  if (n <= 0) return 0;
+  MTVAF_REQUIRE(dst && src, "add_inplace: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(n, 256);
+  if (dst_dtype == MTVAF_BF16 && src_dtype == MTVAF_BF16)
+    add_inplace_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n, alpha);
+  else if (dst_dtype == MTVAF_BF16)
+    add_inplace_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((__nv_bfloat16*)dst, (const float*)src, n, alpha);
+  else if (src_dtype == MTVAF_BF16)
+    add_inplace_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((float*)dst, (const __nv_bfloat16*)src, n, alpha);
+  else
+    add_inplace_kernel<float, float><<<g, 256, 0, st>>>((float*)dst, (const float*)src, n, alpha);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mtvaf_colsum(const void* dy, int64_t ld, int dtype, int M, int N, float* db, void* stream) {
   MTVAF_REQUIRE(dy && db && M > 0 && N > 0, "colsum: bad argument");
   const int col_blocks = (N + 63) / 64;
@@ -210,6 +277,28 @@ extern "C" int mtvaf_mean4_fwd(const void* x, void* y, int64_t rows, int W, int 
 extern "C" int mtvaf_mean4_bwd_add(const float* dy, float* dx, int64_t rows, int W, int mode, void* stream) {
   MTVAF_REQUIRE(dy && dx && rows > 0 && W > 0 && W % 4 == 0, "mean4_bwd: bad argument");
   mean4_bwd_kernel<<<grid_for(rows * 4 * W, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, rows, W, mode);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_rowscale(const void* x, const float* rowscale, void* y, int64_t M, int N, float alpha, int dtype,
+                              void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  MTVAF_REQUIRE(x && rowscale && y, "rowscale: null pointer");
+  const int g = grid_for(M * N, 256);
+  if (dtype == MTVAF_BF16)
+    rowscale_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rowscale,
+                                                                        (__nv_bfloat16*)y, M, N, alpha);
+  else
+    rowscale_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, rowscale, (float*)y, M, N, alpha);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_scale_by_device_scalar(float* x, int64_t n, const float* scalar, void* stream) {
+  if (n <= 0) return 0;
+  MTVAF_REQUIRE(x && scalar, "scale_by_device_scalar: null pointer");
+  scale_dev_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, scalar);
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -79,10 +79,13 @@ __device__ __forceinline__ void epi_store8(void* p, int bf16, long long idx, con
   else Vec8<float>::store(reinterpret_cast<float*>(p) + idx, v);
 }
 
-// scalar math of one output element; `a` = aux value (if the mode uses one)
+// scalar math of one output element; `a` = aux value (if the mode uses one).
+// MODE >= 0 fixes the epilogue at compile time (lean code for the hot kernels); MODE < 0 reads ep.mode.
+template <int MODE = -1>
 __device__ __forceinline__ float epi_math(const EpiArgs& ep, float v, float a, int row, int col, int N,
                                           float& pre_out) {
-  switch (ep.mode) {
+  const int mode = (MODE >= 0) ? MODE : ep.mode;
+  switch (mode) {
     case MTVAF_EPI_GELU: pre_out = v; return gelu_erf(v);
     case MTVAF_EPI_TANH: return tanhf(v);
     case MTVAF_EPI_RESID:
@@ -99,12 +102,13 @@ __device__ __forceinline__ float epi_math(const EpiArgs& ep, float v, float a, i
 }
 
 // One thread owns 32 consecutive columns [col0, col0+32) of output row `row` (tcgen05 epilogue).
+template <int MODE = -1>
 __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t (&r)[32], int row, int col0, int M,
                                                int N, float& rowacc) {
   if (row >= M) return;
-  const bool needs_aux = (ep.mode == MTVAF_EPI_RESID || ep.mode == MTVAF_EPI_MUL_DGELU ||
-                          ep.mode == MTVAF_EPI_MUL_DTANH);
-  const float rs = (ep.mode == MTVAF_EPI_ROWSCALE) ? ep.rowvec[row] : 1.f;
+  const int mode = (MODE >= 0) ? MODE : ep.mode;
+  const bool needs_aux = (mode == MTVAF_EPI_RESID || mode == MTVAF_EPI_MUL_DGELU || mode == MTVAF_EPI_MUL_DTANH);
+  const float rs = (mode == MTVAF_EPI_ROWSCALE) ? ep.rowvec[row] : 1.f;
   const bool full = (col0 + 32 <= N) && ep.vec_ok;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -124,19 +128,19 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         pre[j] = v[j];
-        v[j] = epi_math(ep, v[j], needs_aux ? a[j] : 0.f, row, c + j, N, pre[j]);
+        v[j] = epi_math<MODE>(ep, v[j], needs_aux ? a[j] : 0.f, row, c + j, N, pre[j]);
       }
-      if (ep.mode == MTVAF_EPI_ATOMIC_F32) {
+      if (mode == MTVAF_EPI_ATOMIC_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + c;
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
       } else {
-        if (ep.mode == MTVAF_EPI_SQNORM) {
+        if (mode == MTVAF_EPI_SQNORM) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) rowacc += v[j] * v[j];
         }
         if (ep.out) epi_store8(ep.out, ep.out_bf16, (long long)row * ep.ldo + c, v);
-        if (ep.mode == MTVAF_EPI_GELU && ep.out2) epi_store8(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + c, pre);
+        if (mode == MTVAF_EPI_GELU && ep.out2) epi_store8(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + c, pre);
       }
     } else {
 #pragma unroll
@@ -146,21 +150,23 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t
         float x = v[j] + (ep.bias ? ep.bias[cc] : 0.f);
         float p = x;
         const float av = needs_aux ? epi_load(ep.aux, ep.aux_bf16, (long long)row * ep.ld_aux + cc) : 0.f;
-        x = epi_math(ep, x, av, row, cc, N, p);
-        if (ep.mode == MTVAF_EPI_ATOMIC_F32) {
+        x = epi_math<MODE>(ep, x, av, row, cc, N, p);
+        if (mode == MTVAF_EPI_ATOMIC_F32) {
           atomicAdd(reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + cc, x);
         } else {
-          if (ep.mode == MTVAF_EPI_SQNORM) rowacc += x * x;
+          if (mode == MTVAF_EPI_SQNORM) rowacc += x * x;
           if (ep.out) epi_store(ep.out, ep.out_bf16, (long long)row * ep.ldo + cc, x);
-          if (ep.mode == MTVAF_EPI_GELU && ep.out2) epi_store(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + cc, p);
+          if (mode == MTVAF_EPI_GELU && ep.out2) epi_store(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + cc, p);
         }
       }
     }
   }
 }
 
+template <int MODE = -1>
 __device__ __forceinline__ void epilogue_row_finish(const EpiArgs& ep, int row, int M, float rowacc) {
-  if (ep.mode == MTVAF_EPI_SQNORM && row < M) atomicAdd(ep.rowvec + row, rowacc);
+  const int mode = (MODE >= 0) ? MODE : ep.mode;
+  if (mode == MTVAF_EPI_SQNORM && row < M) atomicAdd(ep.rowvec + row, rowacc);
 }
 
 // element-wise form used by the SIMT fp32 GEMM

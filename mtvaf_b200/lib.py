@@ -38,6 +38,10 @@ SIGNATURES = {
     "mtvaf_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mtvaf_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "mtvaf_colsum": [_vp, _i64, _i, _i, _i, _vp, _vp],
+    "mtvaf_dropout_apply": [_vp, _vp, _i64, _i, _f, _u64, _vp],
+    "mtvaf_rowscale": [_vp, _vp, _vp, _i64, _i, _f, _i, _vp],
+    "mtvaf_scale_by_device_scalar": [_vp, _i64, _vp, _vp],
+    "mtvaf_add_inplace": [_vp, _i, _vp, _i, _i64, _f, _vp],
     "mtvaf_embed_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp,
                            _vp, _f, _u64, _vp],
     "mtvaf_embed_ln_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,

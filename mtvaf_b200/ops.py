@@ -116,6 +116,38 @@ def colsum(dy: torch.Tensor, db: torch.Tensor, n_valid: Optional[int] = None):
     _check(_raw.mtvaf_colsum(dy.data_ptr(), dy.stride(0), dt(dy), dy.shape[0], N, db.data_ptr(), _stream()), "colsum")
 
 
+def dropout_apply(x: torch.Tensor, p_drop: float, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _check(_raw.mtvaf_dropout_apply(x.data_ptr(), out.data_ptr(), x.numel(), dt(x), p_drop, seed, _stream()),
+           "dropout_apply")
+    return out
+
+
+def add_inplace(dst: torch.Tensor, src: torch.Tensor, alpha: float = 1.0):
+    _cuda(dst, src)
+    assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+    _check(_raw.mtvaf_add_inplace(dst.data_ptr(), dt(dst), src.data_ptr(), dt(src), dst.numel(), alpha, _stream()),
+           "add_inplace")
+
+
+def rowscale(x: torch.Tensor, rs: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    _cuda(x, rs)
+    assert x.is_contiguous() and rs.dtype == torch.float32
+    y = torch.empty_like(x)
+    _check(_raw.mtvaf_rowscale(x.data_ptr(), rs.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], alpha, dt(x),
+                               _stream()), "rowscale")
+    return y
+
+
+def scale_by_device_scalar(x: torch.Tensor, s: torch.Tensor):
+    _cuda(x, s)
+    assert x.dtype == torch.float32 and s.dtype == torch.float32 and x.is_contiguous()
+    _check(_raw.mtvaf_scale_by_device_scalar(x.data_ptr(), x.numel(), s.data_ptr(), _stream()), "scale_dev")
+
+
 def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(src)
     assert src.dtype == torch.float32 and src.is_contiguous()
