@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Headline benchmark: MTVAF RoBERTa-base bf16 TRAINING throughput on synthetic Twitter2017-shaped batches
+(BASELINE.json configs[1]) -- one step = forward + backward + gradient sync + AdamW through the drop-in
+TVNetSAModel2 (fusion P=16 + vao + probe + CRF), every op a kernel of mtvaf_b200.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                   (the oracle restatement of the reference on host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L_TEXT = 128
+N_AUX = 3
+ALPHA, BETA = 0.1, 0.5
+LR = 5e-5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mtvaf_b200", choices=["mtvaf_b200", "reference"])
+    ap.add_argument("--per-gpu-batch", type=int, default=int(os.environ.get("MTVAF_BENCH_BATCH", 256)))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    return ap.parse_args()
+
+
+def flops_per_sample_step(L=L_TEXT, P=16, H=768, n=12, n_img=4, vao=True):
+    """training step = 3 x forward algorithmic FLOPs."""
+    Lk = P + L
+    enc = n * L * (24 * H * H + 4 * Lk * H)
+    fusion = n_img * 4 * 2 * (3840 * 800 + 800 * 8 * H) + n * n_img * 2 * 8 * H * 4 + (n_img * 2 * 8 * H * 2089 if vao else 0)
+    probe = 2 * L * H * (H // 2)
+    heads = 2 * L * H * 11
+    return 3 * (enc + fusion + probe + heads)
+
+
+def model_args(dtype):
+    return SimpleNamespace(bert_name="roberta-base", prefix_dim=768, prefix_len=4, use_prefix=True, use_probe=True,
+                           beta=BETA, alpha=ALPHA, vao=True, noauxloss=False, resnet_root=None, compute_dtype=dtype,
+                           n_gpu=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(batch_size: int, steps: int, warmup: int):
+    """The reference's CPU path = the oracle restatement (oracle/mtvaf_oracle.py; the reference itself is
+    Python and does not travel to the GPU box) on all host cores: fwd + bwd of TVNetSAModel2."""
+    from oracle import mtvaf_oracle as O
+    from mtvaf_b200 import synthetic as S
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.EncoderCfg.roberta_base()
+    params = S.init_params(cfg, seed=1)
+    params = {k: v.requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    batch = S.make_batch(batch_size, L_TEXT, shape="twitter2017", seed=2024)
+    times = []
+    for it in range(warmup + steps):
+        for p in params.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        o = O.tvnet2_forward(params, cfg, batch, alpha=ALPHA, beta=BETA)
+        o["loss"].backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return batch_size / med, med, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    v, sec, cores = cpu_reference_run(args.cpu_sample_batch, steps, warm)
+    line = {"impl": "reference", "metric": "train samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MTVAF roberta-base TVNetSAModel2 training step (fusion P=16 + vao + probe + CRF), "
+                                   "Twitter2017-shaped synthetic, L=128; CPU sample batch %d" % args.cpu_sample_batch},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "%d fwd+bwd steps of batch %d, L=128 (oracle restatement of the reference, "
+                                       "fp32, torch CPU eager)" % (steps, args.cpu_sample_batch)},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mtvaf_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle.make_golden import hf_config          # config helper only (no oracle arithmetic)
+    from oracle import mtvaf_oracle as O
+    from mtvaf_b200 import synthetic as S, ops
+    from mtvaf_b200.modules import TVNetSAModel2, FeatureStub
+    from mtvaf_b200.optim import FlatAdamW, GradSync
+
+    B = args.per_gpu_batch
+    cfg = O.EncoderCfg.roberta_base()
+    torch.manual_seed(1234)                              # identical init on every rank
+    model = TVNetSAModel2(list(range(10)), None, model_args(args.dtype), config=hf_config(cfg),
+                          image_model=FeatureStub()).to(dev)
+    model.train()
+    eng = model.engine()
+    eng.base_seed = 0x5EED + rank                        # different dropout streams per rank
+    total_steps = args.warmup + 2 * args.steps + 8
+    opt = FlatAdamW(eng, lr=LR, warmup_steps=max(1, total_steps // 100), total_steps=total_steps * 50)
+    sync = GradSync(eng) if world > 1 else None
+
+    # distinct synthetic batches per rank (DistributedSampler-style disjoint shards), pinned on the host
+    n_host = 4
+    host = []
+    for i in range(n_host):
+        b = S.make_batch(B, L_TEXT, shape="twitter2017", seed=2024 + 100 * rank + i)
+        host.append({k: v.pin_memory() for k, v in b.items()})
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    gemm_events = []
+    ops.GEMM_EVENT_SINK = None
+
+    def step(batch):
+        out, prob, img = model(**batch)
+        out.loss.backward()
+        if sync is not None:
+            sync.finish()
+        opt.step()
+        model.zero_grad(set_to_none=False)
+        return out.loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step(resident[i % n_host])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM -> `value`
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ops.GEMM_EVENT_SINK = gemm_events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(resident[i % n_host])
+    e1.record()
+    barrier()
+    ops.GEMM_EVENT_SINK = None
+    launches = ops.launch_count()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    final_loss = float(loss)
+
+    # dominant kernel: the tcgen05 GEMM.  achieved = algorithmic 2*M*N*K summed over the launches of the
+    # timed region / summed CUDA-event durations of those launches (events recorded on the launch stream)
+    g_fl = sum(f for (_, _, f) in gemm_events)
+    g_ms = sum(a.elapsed_time(b) for (a, b, _) in gemm_events)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+
+    # ---- timed region 2: end to end through the public API with HOST buffers (pinned) -> `e2e`
+    copy_stream = torch.cuda.Stream()
+
+    def h2d(hb):
+        with torch.cuda.stream(copy_stream):
+            d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    nxt = h2d(host[0])
+    for i in range(args.steps):
+        cur, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        if i + 1 < args.steps:
+            nxt = h2d(host[(i + 1) % n_host])            # prefetch the next batch behind this step's compute
+        l = step(cur)
+        loss_host.copy_(l.detach().reshape(()), non_blocking=True)   # D2H read of the step's result
+    e3.record()
+    barrier()
+    t = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+
+    if rank == 0:
+        line = {
+            "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "MTVAF roberta-base TVNetSAModel2 training step (fwd+bwd+grad sync+AdamW; fusion "
+                                   "P=16 + vao + probe + CRF), Twitter2017-shaped synthetic, L=128 (BASELINE.json "
+                                   "configs[1])",
+                       "per_gpu_batch": B, "global_batch": B * world, "seq_len": L_TEXT, "prefix_rows": 16,
+                       "parallelism": "dp%d" % world,
+                       "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "final_loss": final_loss},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05)", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback",
+                         "gemm_launches": len(gemm_events), "gemm_share_of_step": g_ms / ms if ms else None,
+                         "step_model_tflops": flops_per_sample_step() * B / (ms_per_step * 1e-3) / 1e12},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, sec, cores = cpu_reference_run(args.cpu_sample_batch, 3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": "3 fwd+bwd steps of batch %d, L=128 (oracle restatement, fp32 torch "
+                                              "CPU eager; no optimizer step)" % args.cpu_sample_batch}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,8 @@ class FlatParams:
             a = self.offsets[names[0]][0]
             b = self.offsets[names[-1]][0] + self.offsets[names[-1]][1]
             self.layer_ranges.append((a, b))
+        # the pooler is dead on the MTVAF path: like the reference it gets NO gradient
+        self.no_grad_names = {n for n in order if ".pooler." in n or n.startswith("pooler.")}
         self.device = None
         self.W = self.G = self.Wb = None
         self._wb_version = -1
@@ -167,12 +169,20 @@ class FlatParams:
     def attach_grads(self) -> bool:
         """Point param.grad at the flat gradient buffer. Returns True if this starts a fresh
         accumulation (grads were None -> buffer zeroed), False if accumulating into existing grads."""
-        fresh = any(self.params[n].grad is None for n in self.names if self.params[n].requires_grad)
+        if not hasattr(self, "_live"):
+            self._live = [n for n in self.names if self.params[n].requires_grad and n not in self.no_grad_names]
+        live = self._live
+        # fast path (called from every autograd node of the step): first and last live params already attached
+        p0, p1 = self.params[live[0]], self.params[live[-1]]
+        if (p0.grad is not None and p1.grad is not None and p0.grad.data_ptr() == self.g(live[0]).data_ptr()
+                and p1.grad.data_ptr() == self.g(live[-1]).data_ptr()):
+            return False
+        fresh = any(self.params[n].grad is None for n in live)
         if fresh:
             self.G.zero_()
-        for n in self.names:
+        for n in live:
             p = self.params[n]
-            if p.requires_grad:
+            if True:
                 g = self.g(n)
                 if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                     p.grad = g
@@ -200,6 +210,8 @@ class Engine:
         return self.compute_dtype == BF16
 
     def prepare(self):
+        if getattr(self, "_nested", False):      # already prepared by the enclosing model forward
+            return
         dev = next(iter(self.flat.params.values())).device
         self.flat.ensure(dev)
         if self.bf16:

@@ -728,6 +728,14 @@ class TVNetSAModel2(nn.Module):
         eng = self.engine()
         eng.step_counter += 1
         eng.prepare()
+        eng._nested = True
+        try:
+            return self._forward_impl(eng, input_ids, attention_mask, token_type_ids, labels, imagelabel, images,
+                                      aux_imgs)
+        finally:
+            eng._nested = False
+
+    def _forward_impl(self, eng, input_ids, attention_mask, token_type_ids, labels, imagelabel, images, aux_imgs):
         a = self.args
         B, Lq = input_ids.shape
         img_losses = None

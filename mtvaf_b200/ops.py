@@ -32,9 +32,26 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per C-ABI call (default 1): the bench reports the count of OUR launches
+_KERNELS_PER_CALL = {"embed_ln_fwd": 2, "attention_bwd": 3, "gate_bwd": 2, "mse": 1}
+_launches = 0
+GEMM_EVENT_SINK = None      # bench.py: list receiving (start_event, end_event, flops) per tcgen05 GEMM launch
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
 def _check(rc: int, name: str):
+    global _launches
     if rc != 0:
         raise L.MtvafError("%s failed (%d): %s" % (name, rc, L.last_error()))
+    _launches += _KERNELS_PER_CALL.get(name, 1)
 
 
 def _cuda(*ts):
@@ -76,8 +93,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if aux is not None:
         assert aux.dtype == a.dtype
     fn = _raw.mtvaf_gemm_bf16 if a.dtype == torch.bfloat16 else _raw.mtvaf_gemm_f32
+    sink = GEMM_EVENT_SINK if a.dtype == torch.bfloat16 else None
+    if sink is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = fn(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), M, N, K, C.byref(ep),
             splits, _stream())
+    if sink is not None:
+        e1.record()
+        sink.append((e0, e1, 2.0 * M * N * K))
     _check(rc, "mtvaf_gemm")
     return out
 
@@ -96,9 +121,15 @@ def wgrad_splits(m_out: int, n_out: int, k: int, bf16: bool) -> int:
     bm, bn = (128, 256 if n_out > 128 else 128) if bf16 else (128, 128)
     tiles = ((m_out + bm - 1) // bm) * ((n_out + bn - 1) // bn)
     kb = max(1, k // (64 if bf16 else 16))
-    target = 148 * (1 if bf16 else 2)
-    s = max(1, min(kb, (target + tiles - 1) // tiles))
-    return s
+    slots = 148 * (1 if bf16 else 2)          # persistent CTAs (bf16) / resident blocks (fp32)
+    best, best_score = 1, -1.0
+    for s in range(1, min(kb, 32) + 1):
+        items = tiles * s
+        waves = (items + slots - 1) // slots
+        score = items / float(waves * slots) - 0.01 * s      # wave efficiency, mild penalty for atomics traffic
+        if score > best_score:
+            best, best_score = s, score
+    return best
 
 
 def linear_wgrad(dy, x, dw: torch.Tensor, *, n_valid: Optional[int] = None):

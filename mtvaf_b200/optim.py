@@ -1,0 +1,131 @@
+"""Fused AdamW over the flat parameter buffer + per-rank gradient synchronisation.
+
+Replaces `torch.optim.AdamW` with the reference's parameter groups (modules/train.py:894-926: names
+containing 'bert' and 'encoder_conv' at args.lr, 'crf'/'fc*' at 5e-2, weight decay 1e-2, everything
+else -- projectors, ANP heads, probe -- never updated), the linear warm-up/decay schedule
+(`get_linear_schedule_with_warmup`, modules/train.py:118-120,919-921) and the broken
+`modules/parallel.py` path: one process per GPU, NCCL all-reduce of the flat gradient buffer issued per
+encoder layer from inside backward so it overlaps the remaining backward kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .engine import Engine, BF16, F32
+
+
+def reference_groups(lr: float):
+    """(predicate on parameter name, lr, weight_decay) exactly as modules/train.py:896-916."""
+    return [(lambda n: "bert" in n, lr, 1e-2),
+            (lambda n: "encoder_conv" in n or "gates" in n, lr, 1e-2),
+            (lambda n: "crf" in n or n.startswith("fc"), 5e-2, 1e-2)]
+
+
+class FlatAdamW:
+    def __init__(self, engine: Engine, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, groups=None,
+                 warmup_steps: int = 0, total_steps: int = 0):
+        self.engine = engine
+        engine.prepare()
+        f = engine.flat
+        self.betas, self.eps = betas, eps
+        self.warmup_steps, self.total_steps = warmup_steps, total_steps
+        groups = groups if groups is not None else reference_groups(lr)
+        # contiguous [start, end) ranges of the flat buffer sharing (lr, wd)
+        self.ranges: List[Tuple[int, int, float, float]] = []
+        cur = None
+        for n in f.names:
+            p = f.params[n]
+            hit = None
+            if p.requires_grad and n not in f.no_grad_names:
+                for pred, glr, gwd in groups:
+                    if pred(n):
+                        hit = (glr, gwd)
+                        break
+            o, k = f.offsets[n]
+            if hit is None:
+                cur = None
+                continue
+            if cur is not None and cur[2:] == hit and o - cur[1] < 64:
+                cur[1] = o + k
+            else:
+                cur = [o, o + k, hit[0], hit[1]]
+                self.ranges.append(cur)
+        self.m = torch.zeros(f.total, dtype=F32, device=f.device)
+        self.v = torch.zeros(f.total, dtype=F32, device=f.device)
+        self.t = 0
+
+    def lr_scale(self) -> float:
+        """get_linear_schedule_with_warmup evaluated for the step about to be taken."""
+        if self.total_steps <= 0:
+            return 1.0
+        s = self.t
+        if s < self.warmup_steps:
+            return s / max(1.0, float(self.warmup_steps))
+        return max(0.0, (self.total_steps - s) / max(1.0, float(self.total_steps - self.warmup_steps)))
+
+    def step(self, grad_scale: float = 1.0):
+        f = self.engine.flat
+        scale = self.lr_scale()
+        self.t += 1
+        bf = self.engine.bf16 and f.Wb is not None
+        for a, b, lr, wd in self.ranges:
+            shadow = None
+            if bf and b <= f.cast_end:
+                shadow = f.Wb[a:b]
+            ops.adamw_step(f.W[a:b], f.G[a:b], self.m[a:b], self.v[a:b], lr * scale, self.betas[0], self.betas[1],
+                           self.eps, wd, self.t, grad_scale, shadow)
+        if bf:
+            f._wb_version = f.weights_version()     # shadow written by the fused kernel: still in sync
+
+    def zero_grad(self):
+        self.engine.flat.G.zero_()
+
+
+class GradSync:
+    """NCCL gradient all-reduce (average) of the flat gradient buffer, per encoder layer, overlapped
+    with backward.  Usage: sync = GradSync(engine); loss.backward(); sync.finish(); optimizer.step()."""
+
+    def __init__(self, engine: Engine, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.works = []
+        self.done_layers = set()
+        self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
+        if self.world > 1:
+            engine.layer_grad_hook = self._on_layer
+
+    def _reduce(self, t: torch.Tensor):
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.works.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True))
+
+    def _on_layer(self, i: int):
+        a, b = self.engine.flat.layer_ranges[i]
+        self.done_layers.add(i)
+        self._reduce(self.engine.flat.G[a:b])
+
+    def finish(self):
+        """Reduce everything outside the per-layer slices (heads, fusion, embeddings), then wait."""
+        if self.world <= 1:
+            return
+        f = self.engine.flat
+        lo = f.layer_ranges[-1][1] if f.layer_ranges else 0
+        first = f.layer_ranges[0][0] if f.layer_ranges else 0
+        if first > 0:
+            self._reduce(f.G[:first])
+        for i, (a, b) in enumerate(f.layer_ranges):
+            if i not in self.done_layers:
+                self._reduce(f.G[a:b])
+        self._reduce(f.G[lo:])
+        for w in self.works:
+            w.wait()
+        self.works.clear()
+        self.done_layers.clear()

@@ -84,7 +84,7 @@ def test_tvnet2_fp32_matches_reference_golden(golden_dir):
     assert agree >= 0.999
     # ---- backward parity
     out.loss.backward()
-    fp = grad_fingerprint([(k, p.grad) for k, p in m.named_parameters()])
+    fp = grad_fingerprint([(k, None if p.grad is None else p.grad.cpu()) for k, p in m.named_parameters()])
     check_fp(fp, g["grad_fp"], 2e-3)
 
 
@@ -126,7 +126,7 @@ def test_encoder_fp32_matches_reference_golden(golden_dir, name):
     w12 = torch.randn(hs[12].shape, generator=gen).to(DEV)
     obj = (hs[7] * w7).sum() + (hs[12] * w12).sum()
     obj.backward()
-    fp = grad_fingerprint([("bert." + k, p.grad) for k, p in m.named_parameters()])
+    fp = grad_fingerprint([("bert." + k, None if p.grad is None else p.grad.cpu()) for k, p in m.named_parameters()])
     check_fp(fp, g["grad_fp"], 2e-3)
     if P:
         assert rel(pkv[0][0].grad, g["dk0"]) < 1e-3
