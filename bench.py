@@ -237,7 +237,7 @@ def main():
     ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # dominant kernel: the tcgen05 GEMM.  achieved = algorithmic 2*M*N*K summed over the launches of the
     # timed region / summed CUDA-event durations of those launches (events recorded on the launch stream)
@@ -269,6 +269,8 @@ def main():
     for i in range(args.steps):
         cur, ev = nxt
         torch.cuda.current_stream().wait_event(ev)
+        for v in cur.values():                            # allocated on the copy stream, consumed on this one
+            v.record_stream(torch.cuda.current_stream())
         if i + 1 < args.steps:
             nxt = h2d(host[(i + 1) % n_host])            # prefetch the next batch behind this step's compute
         l = step(cur)
