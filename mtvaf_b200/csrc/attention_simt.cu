@@ -9,6 +9,7 @@
 // (b,h,q,k) so backward regenerates the same mask.
 #include "common.cuh"
 #include "../../include/mtvaf_b200.h"
+#include "attention_tc.cuh"
 
 namespace mtvaf {
 
@@ -477,6 +478,14 @@ static int fill_args(AttnArgs* a, const void* qkv, int64_t ld_qkv, const void* k
 
 using namespace mtvaf;
 
+static int g_attention_impl = 0;
+namespace mtvaf { int attention_impl_override() { return g_attention_impl; } }
+extern "C" int mtvaf_set_attention_impl(int impl) {
+  MTVAF_REQUIRE(impl == 0 || impl == 1, "attention impl must be 0 (auto) or 1 (SIMT)");
+  g_attention_impl = impl;
+  return 0;
+}
+
 extern "C" int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P,
                                    const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx,
                                    float* lse, float* probs, int dtype, float p_drop, uint64_t seed, void* stream) {
@@ -485,9 +494,23 @@ extern "C" int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* 
   MTVAF_REQUIRE(ctx && lse, "attention_fwd: null output");
   dim3 grid((L + AQB - 1) / AQB, nh, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MTVAF_BF16) attn_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a, (__nv_bfloat16*)ctx, ld_ctx, lse);
-  else attn_fwd_kernel<float><<<grid, 128, 0, st>>>(a, (float*)ctx, ld_ctx, lse);
-  MTVAF_LAUNCH_CHECK();
+  bool done = false;
+  if (dtype == MTVAF_BF16 && attention_impl_override() == 0 && ld_ctx % 8 == 0) {
+    // tensor-core path (tcgen05): every shape of the benchmark configs; others fall through to SIMT
+    AttnTcArgs ta;
+    AttnTcMaps tm;
+    bool ok = false;
+    if (int rc = attn_tc_prepare(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, p_drop, seed, &ta, &tm, &ok)) return rc;
+    if (ok) {
+      if (int rc = attn_fwd_tc_launch(ta, tm, ctx, ld_ctx, lse, st)) return rc;
+      done = true;
+    }
+  }
+  if (!done) {
+    if (dtype == MTVAF_BF16) attn_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a, (__nv_bfloat16*)ctx, ld_ctx, lse);
+    else attn_fwd_kernel<float><<<grid, 128, 0, st>>>(a, (float*)ctx, ld_ctx, lse);
+    MTVAF_LAUNCH_CHECK();
+  }
   if (probs) {
     dim3 g2(L, nh, B);
     if (dtype == MTVAF_BF16) attn_probs_kernel<__nv_bfloat16><<<g2, 128, 0, st>>>(a, lse, probs);

@@ -1,0 +1,33 @@
+// Shared declarations of the tcgen05 prefix-attention kernels (forward: attention_tc.cu, backward:
+// attention_tc_bwd.cu) and of the SIMT implementation they fall back to for shapes they do not cover.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/mtvaf_b200.h"
+
+namespace mtvaf {
+
+struct AttnTcArgs {
+  int P, P8;            // prefix rows, padded to a multiple of 8 in the shared-memory key numbering
+  int L, L64;           // text rows, padded to a multiple of 64 (TMA box rows)
+  int N16;              // keys covered by the MMAs: round16(P8 + L)
+  int B, nh;
+  const long long* key_mask;
+  float scale;
+  uint32_t drop_thr; float drop_scale; unsigned long long seed;
+};
+
+struct AttnTcMaps {
+  CUtensorMap q, kv, kp, vp, dq, dkv;   // q/dq: 128-row boxes, kv/dkv: 64-row boxes, kp/vp: 8-row boxes
+};
+
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer);
+
+int attn_tc_prepare(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P, const int64_t* key_mask,
+                    int B, int L, int nh, float p_drop, uint64_t seed, AttnTcArgs* a, AttnTcMaps* m, bool* ok);
+int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int64_t ld_ctx, float* lse,
+                       cudaStream_t st);
+int attention_impl_override();   // 0 = auto (tcgen05 when the shape fits), 1 = SIMT only
+
+}  // namespace mtvaf

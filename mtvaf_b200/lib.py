@@ -49,6 +49,7 @@ SIGNATURES = {
     "mtvaf_layernorm_fwd": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp],
     "mtvaf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mtvaf_attention_fwd": [_vp, _i64, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _f, _u64, _vp],
+    "mtvaf_set_attention_impl": [_i],
     "mtvaf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp,
                             _vp, _vp, _i, _f, _u64, _vp],
     "mtvaf_gate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],

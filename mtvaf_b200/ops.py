@@ -247,6 +247,11 @@ def embed_ln_bwd(dout, ids, tts, pids, word, pos, typ, gamma, mean, rstd, kind, 
 
 
 # ------------------------------------------------------------------------------------------ attention
+def set_attention_impl(impl: str):
+    """'auto' (tcgen05 kernels when bf16 and the shape fits) or 'simt' (A/B testing)."""
+    _check(_raw.mtvaf_set_attention_impl({"auto": 0, "simt": 1}[impl]), "set_attention_impl")
+
+
 def attention_fwd(qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.0, seed=0, want_probs=False):
     _cuda(qkv, key_mask)
     P = 0 if kp is None else kp.shape[2]

@@ -48,7 +48,7 @@ class FlatAdamW:
             if hit is None:
                 cur = None
                 continue
-            if cur is not None and cur[2:] == hit and o - cur[1] < 64:
+            if cur is not None and tuple(cur[2:]) == hit and o - cur[1] < 64:
                 cur[1] = o + k
             else:
                 cur = [o, o + k, hit[0], hit[1]]
