@@ -45,6 +45,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     fence_barrier_init();
   }
+  __syncwarp();                                      // tcgen05.alloc is .sync.aligned: reconverge warp 0 first
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
   // additive key mask in smem-key numbering: prefix rows [0,P) visible, [P,P8) padding, text rows follow
   for (int k = tid; k < a.N16; k += 128) {
@@ -89,6 +90,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   __syncwarp();
   mbar_wait(&bars[1], 0);
+  __syncwarp();
   tc_fence_after();
 
   // ---- softmax over this thread's row of S (two passes over TMEM)
@@ -156,38 +158,35 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   __syncwarp();
   mbar_wait(&bars[2], 0);
+  __syncwarp();
   tc_fence_after();
 
+  // tcgen05.ld is warp-collective (.sync.aligned): EVERY lane issues the loads (rows past L included,
+  // never inside a divergent branch); only the global stores are predicated.
   const float inv = 1.f / sum;
-  if (q < a.L) {
-    __nv_bfloat16* o = ctx + ((long long)b * a.L + q) * ld_ctx + h * 64;
+  const bool valid = q < a.L;
+  __nv_bfloat16* o = ctx + ((long long)b * a.L + (valid ? q : 0)) * ld_ctx + h * 64;
 #pragma unroll
-    for (int c = 0; c < 64; c += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_row + S_COLS + c, r);
-      tmem_ld_wait();
-      uint4 u0, u1;
-      u0.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-      u0.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-      u0.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-      u0.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-      u1.x = pack_bf16x2(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
-      u1.y = pack_bf16x2(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
-      u1.z = pack_bf16x2(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
-      u1.w = pack_bf16x2(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+  for (int c = 0; c < 64; c += 16) {
+    uint32_t r[16];
+    __syncwarp();
+    tmem_ld_32x32b_x16(t_row + S_COLS + c, r);
+    tmem_ld_wait();
+    uint4 u0, u1;
+    u0.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+    u0.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+    u0.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+    u0.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+    u1.x = pack_bf16x2(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+    u1.y = pack_bf16x2(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+    u1.z = pack_bf16x2(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+    u1.w = pack_bf16x2(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+    if (valid) {
       *reinterpret_cast<uint4*>(o + c) = u0;
       *reinterpret_cast<uint4*>(o + c + 8) = u1;
     }
-    lse_out[((long long)b * a.nh + h) * a.L + q] = mx + __logf(sum);
-  } else {
-    // tcgen05.ld is warp-collective (.sync.aligned): rows past L still take part
-#pragma unroll
-    for (int c = 0; c < 64; c += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_row + S_COLS + c, r);
-      tmem_ld_wait();
-    }
   }
+  if (valid) lse_out[((long long)b * a.nh + h) * a.L + q] = mx + __logf(sum);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
