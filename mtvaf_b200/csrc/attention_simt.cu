@@ -531,6 +531,17 @@ extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void
   cudaStream_t st = (cudaStream_t)stream;
   const int total = B * nh * L;
   dim3 gq((L + AQB - 1) / AQB, nh, B), gk((P + L + AQB - 1) / AQB, nh, B);
+  if (dtype == MTVAF_BF16 && attention_impl_override() == 0 && ld_ctx % 8 == 0 && ld_dctx % 8 == 0 &&
+      ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(dctx) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0) {
+    // tensor-core path (tcgen05): one CTA per (batch, head), L <= 128
+    AttnTcArgs ta;
+    AttnTcMaps tm;
+    bool ok = false;
+    if (int rc = attn_tc_prepare(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, p_drop, seed, &ta, &tm, &ok)) return rc;
+    if (ok && attn_bwd_tc_supported(ta))
+      return attn_bwd_tc_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st);
+  }
   if (dtype == MTVAF_BF16) {
     using T = __nv_bfloat16;
     attn_dsum_kernel<T><<<(total * 32 + 255) / 256, 256, 0, st>>>((const T*)dctx, ld_dctx, (const T*)ctx, ld_ctx, B, L, nh, dsum_scratch);

@@ -57,6 +57,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     sMask[k] = m;
   }
+  // K rows [key_rows, N16) alias the first V rows and V rows [key_rows, N16) alias the first rows of sP:
+  // both hold finite bf16 values, and those key columns get p = 0 (mask -inf), so they contribute nothing.
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -28,6 +28,10 @@ int attn_tc_prepare(const void* qkv, int64_t ld_qkv, const void* kp, const void*
                     int B, int L, int nh, float p_drop, uint64_t seed, AttnTcArgs* a, AttnTcMaps* m, bool* ok);
 int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int64_t ld_ctx, float* lse,
                        cudaStream_t st);
+bool attn_bwd_tc_supported(const AttnTcArgs& a);
+int attn_bwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
+                       int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
+                       cudaStream_t st);
 int attention_impl_override();   // 0 = auto (tcgen05 when the shape fits), 1 = SIMT only
 
 }  // namespace mtvaf

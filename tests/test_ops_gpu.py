@@ -273,6 +273,39 @@ def test_attention_dropout_consistency(ops):
     assert abs(float(fd) - float(dvp[1, 3, 5, 7])) < 1e-3 * (1 + abs(float(fd)))
 
 
+@pytest.mark.parametrize("B,Lq,P,p_drop", [(2, 128, 16, 0.1), (3, 40, 36, 0.1), (2, 100, 5, 0.0), (4, 128, 64, 0.1),
+                                            (2, 128, 0, 0.1), (1, 17, 4, 0.0)])
+def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
+    """The tcgen05 forward/backward kernels and the SIMT kernels share one dropout hash: on bf16 inputs they
+    must agree to bf16 rounding, with and without probability dropout, including ragged key masks."""
+    nh, d = 12, 64
+    bf = torch.bfloat16
+    qkv = rnd(B * Lq, 3 * nh * d, seed=11, dtype=bf)
+    kp = rnd(B, nh, P, d, seed=12, dtype=bf) if P else None
+    vp = rnd(B, nh, P, d, seed=13, dtype=bf) if P else None
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(3, Lq + 1, (B,), generator=g)
+    mask = (torch.arange(Lq)[None] < lens[:, None]).long().to(DEV)
+    dctx = rnd(B * Lq, nh * d, seed=14, dtype=bf)
+    res = {}
+    try:
+        for impl in ("simt", "auto"):
+            ops.set_attention_impl(impl)
+            ctx, lse, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p_drop, seed=99)
+            dkp = torch.zeros(B, nh, P, d, device=DEV) if P else None
+            dvp = torch.zeros(B, nh, P, d, device=DEV) if P else None
+            dqkv = ops.attention_bwd(dctx, qkv, kp, vp, mask, ctx, lse, B, Lq, nh, d, dkp, dvp, p_drop=p_drop, seed=99)
+            res[impl] = (ctx, lse, dqkv, dkp, dvp)
+    finally:
+        ops.set_attention_impl("auto")
+    names = ("ctx", "lse", "dqkv", "dkp", "dvp")
+    for nm, a, b in zip(names, res["auto"], res["simt"]):
+        if a is None:
+            continue
+        assert torch.isfinite(a.float()).all(), nm
+        assert rel_err(a, b) < 2e-2, nm
+
+
 # ---------------------------------------------------------------------------------------- fusion
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gate_and_mean4(ops, dtype):
