@@ -75,6 +75,9 @@ typedef struct MtvafEpilogue {
  * `splits` > 1 partitions K over CTAs (only with MTVAF_EPI_ATOMIC_F32 / SQNORM is that meaningful). */
 int mtvaf_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                     int M, int N, int K, const MtvafEpilogue* epi, int splits, void* stream);
+/* 0 (default) = CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) whenever M >= 256, single-CTA
+ * 128 x 256 tiles otherwise; 1 = single-CTA kernel only (A/B testing). */
+int mtvaf_set_gemm_impl(int impl);
 /* fp32 operands, fp32 FFMA (parity mode; also used for skinny heads such as fc 768->11). */
 int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, const MtvafEpilogue* epi, int splits, void* stream);

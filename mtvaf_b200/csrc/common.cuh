@@ -123,18 +123,46 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + ~12 FMA-class ops,
+// used by the bf16 tensor-core epilogues (results are rounded to bf16, eps 3.9e-3); the fp32 parity path
+// keeps erff.  `e_out` = exp(-x^2/2), shared with the Gaussian pdf of GELU'.
+__device__ __forceinline__ float normal_cdf_fast(float x, float& e_out) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  e_out = e;
+  const float half_erfc = 0.5f * p * e;             // 0.5 * erfc(|x|/sqrt2)
+  return x >= 0.f ? 1.f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  return x * normal_cdf_fast(x, e);
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float e;
+  const float cdf = normal_cdf_fast(x, e);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
 // ---- dropout: counter-based hash RNG, recomputed (never stored) in backward ----------------------
 // keep(seed, stream, idx) is a pure function; `stream` separates the dropout sites of one step.
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
-  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-  return h;
-}
 __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
-  uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
-  uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
-  uint32_t h = mix32(lo ^ s0);
-  h = mix32(h + 0x9e3779b9u * (hi + 1u) + s1);
-  return mix32(h ^ (lo * 0x27d4eb2fu));
+  // 3 multiply / xor-shift rounds over (idx, seed): ~11 integer ops per element (the epilogues and the
+  // attention softmax are issue-bound, so the mask must be cheap); plenty for a Bernoulli mask
+  const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
+  const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t h = (lo ^ s0) * 0x9E3779B1u;
+  h ^= h >> 15;
+  h = (h ^ (hi * 0x85EBCA77u + s1)) * 0xC2B2AE3Du;
+  h ^= h >> 13;
+  h *= 0x27D4EB2Fu;
+  h ^= h >> 16;
+  return h;
 }
 // threshold = round(p * 2^32) (clamped); element is KEPT iff bits >= threshold
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {

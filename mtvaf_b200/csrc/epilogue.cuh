@@ -13,6 +13,7 @@ struct EpiArgs {
   int out_bf16;        // 1: out/out2 are bf16, 0: fp32
   int aux_bf16;        // dtype of aux
   int vec_ok;          // all pointers / leading dims allow 8-wide vector access
+  int staged;          // bf16 out/out2/aux, 16-byte aligned, ld % 8 == 0: eligible for the TMA-staged epilogue
   void* out;
   long long ldo;
   const float* bias;
@@ -59,6 +60,7 @@ inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N
   };
   o->vec_ok = al(o->out, o->ldo, o->out_bf16) && al(o->aux, o->ld_aux, o->aux_bf16) &&
               al(o->out2, o->ld_out2, o->out_bf16) && (!o->bias || reinterpret_cast<uintptr_t>(o->bias) % 16 == 0);
+  o->staged = o->vec_ok && o->out_bf16 && o->out != nullptr && (!o->aux || o->aux_bf16) && splits <= 1;
   return 0;
 }
 
@@ -81,12 +83,12 @@ __device__ __forceinline__ void epi_store8(void* p, int bf16, long long idx, con
 
 // scalar math of one output element; `a` = aux value (if the mode uses one).
 // MODE >= 0 fixes the epilogue at compile time (lean code for the hot kernels); MODE < 0 reads ep.mode.
-template <int MODE = -1>
+template <int MODE = -1, bool FAST = false>
 __device__ __forceinline__ float epi_math(const EpiArgs& ep, float v, float a, int row, int col, int N,
                                           float& pre_out) {
   const int mode = (MODE >= 0) ? MODE : ep.mode;
   switch (mode) {
-    case MTVAF_EPI_GELU: pre_out = v; return gelu_erf(v);
+    case MTVAF_EPI_GELU: pre_out = v; return FAST ? gelu_fast(v) : gelu_erf(v);
     case MTVAF_EPI_TANH: return tanhf(v);
     case MTVAF_EPI_RESID:
       if (ep.drop_threshold) {
@@ -95,7 +97,7 @@ __device__ __forceinline__ float epi_math(const EpiArgs& ep, float v, float a, i
         v = keep ? v * ep.drop_scale : 0.f;
       }
       return v + a;
-    case MTVAF_EPI_MUL_DGELU: return v * dgelu_erf(a);
+    case MTVAF_EPI_MUL_DGELU: return v * (FAST ? dgelu_fast(a) : dgelu_erf(a));
     case MTVAF_EPI_MUL_DTANH: return v * (1.f - a * a);
     default: return v;
   }

@@ -1,0 +1,81 @@
+// Coalesced GEMM epilogue for the CTA-pair tcgen05 kernel: every epilogue warp owns a [32 rows x 64 cols]
+// bf16 box of the output tile at a time.  The residual / pre-activation operand of the fused epilogues
+// (models/modeling_roberta.py:297-298,366 and their backward) arrives by TMA into a per-warp
+// SWIZZLE_128B box (double buffered, prefetched two boxes ahead), the results are written to a per-warp
+// staging box in shared memory (conflict-free 16-byte pieces) and leave with ONE TMA store per box, so
+// global traffic is full 128-byte lines instead of 32 scattered 16-byte pieces per warp instruction.
+#pragma once
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace mtvaf {
+
+constexpr int kEpiBoxBytes = 32 * 128;     // 32 rows x 64 bf16
+
+template <int MODE>
+struct StagedEpi {
+  static constexpr bool kStaged = (MODE == MTVAF_EPI_STORE || MODE == MTVAF_EPI_GELU || MODE == MTVAF_EPI_TANH ||
+                                   MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU ||
+                                   MODE == MTVAF_EPI_MUL_DTANH);
+  static constexpr bool kAux = (MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU || MODE == MTVAF_EPI_MUL_DTANH);
+  static constexpr int kOutBufs = kStaged ? ((MODE == MTVAF_EPI_GELU) ? 2 : 1) : 0;
+  static constexpr int kAuxBufs = kAux ? 2 : 0;
+  static constexpr int kBytesPerWarp = (kOutBufs + kAuxBufs) * kEpiBoxBytes;
+};
+
+// math of one 32-column chunk of one row: acc (TMEM registers) -> packed bf16 pairs.
+// aux4: the thread's 4 x 16-byte pieces (32 bf16) of the auxiliary operand, already in registers.
+template <int MODE>
+__device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t (&r)[32], const uint4 (&aux4)[4],
+                                              int row, int col0, int N, uint32_t (&outp)[16], uint32_t (&prep)[16]) {
+  constexpr bool needs_aux = StagedEpi<MODE>::kAux;
+  const bool full = (col0 + 32 <= N);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8], a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+    if (ep.alpha != 1.f) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= ep.alpha;
+    }
+    if (ep.bias) {
+      const int c = col0 + g * 8;
+      if (full) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < N) v[j] += __ldg(ep.bias + c + j);
+      }
+    }
+    if (needs_aux) {
+      const float2 a0 = unpack_bf16x2(aux4[g].x), a1 = unpack_bf16x2(aux4[g].y), a2 = unpack_bf16x2(aux4[g].z),
+                   a3 = unpack_bf16x2(aux4[g].w);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float pre = v[j];
+      o[j] = epi_math<MODE, true>(ep, v[j], needs_aux ? a[j] : 0.f, row, col0 + g * 8 + j, N, pre);
+      v[j] = pre;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) outp[g * 4 + j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
+    if (MODE == MTVAF_EPI_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) prep[g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    }
+  }
+}
+
+// byte offset of 16-byte piece `c16` (0..7) of row `row` (0..31) inside a SWIZZLE_128B [32][64 bf16] box
+__device__ __forceinline__ uint32_t box_piece_off(int row, int c16) {
+  return static_cast<uint32_t>(row * 128 + ((c16 ^ (row & 7)) << 4));
+}
+
+}  // namespace mtvaf

@@ -1,5 +1,5 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction and the C-ABI entry point.
-#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 namespace mtvaf {
 
@@ -42,6 +42,14 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 }  // namespace mtvaf
 
 using namespace mtvaf;
+
+static int g_gemm_impl = 0;
+namespace mtvaf { int gemm_impl_override() { return g_gemm_impl; } }
+extern "C" int mtvaf_set_gemm_impl(int impl) {
+  MTVAF_REQUIRE(impl == 0 || impl == 1, "gemm impl must be 0 (auto: CTA pairs) or 1 (single-CTA tiles)");
+  g_gemm_impl = impl;
+  return 0;
+}
 
 extern "C" int mtvaf_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                                int b_mn_major, int M, int N, int K, const MtvafEpilogue* epi, int splits,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mtvaf_abi_version": [],
     "mtvaf_device_info": [_vp, _vp, _vp],
     "mtvaf_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
+    "mtvaf_set_gemm_impl": [_i],
     "mtvaf_gemm_f32": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
     "mtvaf_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mtvaf_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],

@@ -107,6 +107,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+def set_gemm_impl(impl: str):
+    """'auto' (CTA-pair cta_group::2 kernel when M >= 256) or 'single' (single-CTA tiles; A/B testing)."""
+    global _GEMM_PAIR
+    _check(_raw.mtvaf_set_gemm_impl({"auto": 0, "single": 1}[impl]), "set_gemm_impl")
+    _GEMM_PAIR = impl == "auto"
+
+
+_GEMM_PAIR = True
+
+
 def linear_fwd(x, w, bias=None, **kw):
     """y = x w^T + b  (x [M,K], w [N,K])"""
     return gemm(x, w, M=x.shape[0], N=w.shape[0], K=x.shape[1], bias=bias, **kw)
@@ -119,9 +129,11 @@ def linear_dgrad(dy, w, **kw):
 
 def wgrad_splits(m_out: int, n_out: int, k: int, bf16: bool) -> int:
     bm, bn = (128, 256 if n_out > 128 else 128) if bf16 else (128, 128)
+    slots = 148 * (1 if bf16 else 2)          # persistent CTAs (bf16) / resident blocks (fp32)
+    if bf16 and _GEMM_PAIR and m_out >= 256:
+        bm, slots = 256, 74                   # CTA-pair kernel: 256-row tiles, one cluster per TPC
     tiles = ((m_out + bm - 1) // bm) * ((n_out + bn - 1) // bn)
     kb = max(1, k // (64 if bf16 else 16))
-    slots = 148 * (1 if bf16 else 2)          # persistent CTAs (bf16) / resident blocks (fp32)
     best, best_score = 1, -1.0
     for s in range(1, min(kb, 32) + 1):
         items = tiles * s

@@ -143,6 +143,51 @@ def test_gemm_bf16_large_persistent(ops, Lb):
     assert rel_err(y, ref) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(5000, 800, 768), (4096, 2304, 768), (1111, 768, 3072), (2048, 72, 256)])
+def test_gemm_pair_kernel_matches_single(ops, Lb, M, N, K):
+    """CTA-pair (cta_group::2) kernel with the TMA-staged epilogue vs the single-CTA kernel with direct stores:
+    ragged M / N, many tiles per cluster, every fused epilogue of the training step, same dropout mask."""
+    bf = torch.bfloat16
+    x = rnd(M, K, seed=31, dtype=bf)
+    w = rnd(N, K, seed=32, scale=0.05, dtype=bf)
+    bias = rnd(N, seed=33)
+    res = rnd(M, N, seed=34, dtype=bf)
+    dy = rnd(M, N, seed=35, dtype=bf)
+    ref = x.float() @ w.float().t() + bias
+    out = {}
+    try:
+        for impl in ("single", "auto"):
+            ops.set_gemm_impl(impl)
+            pre = torch.empty(M, N, dtype=bf, device=DEV)
+            o = dict(store=ops.linear_fwd(x, w, bias),
+                     gelu=ops.linear_fwd(x, w, bias, mode=Lb.EPI_GELU, out2=pre), pre=pre,
+                     tanh=ops.linear_fwd(x, w, bias, mode=Lb.EPI_TANH),
+                     resid=ops.linear_fwd(x, w, bias, mode=Lb.EPI_RESID, aux=res),
+                     drop=ops.linear_fwd(x, w, bias, mode=Lb.EPI_RESID, aux=res, p_drop=0.1, seed=4321),
+                     dgelu=ops.linear_fwd(x, w, None, mode=Lb.EPI_MUL_DGELU, aux=res),
+                     dtanh=ops.linear_fwd(x, w, None, mode=Lb.EPI_MUL_DTANH, aux=torch.tanh(res.float()).to(bf)),
+                     dgrad=ops.linear_dgrad(dy, w),
+                     f32=ops.linear_fwd(x, w, bias, out_dtype=torch.float32))
+            dw = torch.zeros(N, K, device=DEV)
+            ops.linear_wgrad(dy, x, dw)
+            o["wgrad"] = dw
+            out[impl] = o
+    finally:
+        ops.set_gemm_impl("auto")
+    assert rel_err(out["auto"]["store"], ref) < 1e-2
+    assert rel_err(out["auto"]["gelu"], F.gelu(ref)) < 1e-2
+    assert rel_err(out["auto"]["resid"], ref + res.float()) < 1e-2
+    assert rel_err(out["auto"]["wgrad"], dy.float().t() @ x.float()) < 1e-2
+    for k in out["auto"]:
+        a, b = out["auto"][k], out["single"][k]
+        assert torch.isfinite(a.float()).all(), k
+        assert rel_err(a, b) < 1e-2, k
+    # identical dropout masks in both kernels
+    za, zb = out["auto"]["drop"].float() == res.float(), out["single"]["drop"].float() == res.float()
+    assert torch.equal(za, zb)
+    assert abs(float((~za).float().mean()) - 0.9) < 0.01
+
+
 # ---------------------------------------------------------------------------------------- LN / embeddings
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("H", [768, 1024])

@@ -1,8 +1,10 @@
-"""Micro-benchmark of the tcgen05 GEMM (CUDA events, L2 flushed between iterations)."""
+"""Micro-benchmark of the tcgen05 GEMMs (CUDA events, L2 flushed between iterations), per implementation
+('single' = 128x256 single-CTA tiles, 'auto' = CTA-pair cta_group::2 kernel) next to cuBLAS (torch.matmul)."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mtvaf_b200 import ops, lib as Lb
+
 
 def timeit(fn, iters=20, warm=3):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -17,27 +19,42 @@ def timeit(fn, iters=20, warm=3):
     ts.sort()
     return ts[len(ts) // 2]
 
+
 def main():
     T = int(os.environ.get("T", 32768))
+    impls = os.environ.get("IMPLS", "single,auto").split(",")
     res = []
-    for name, (M, N, K) in {"qkv": (T, 2304, 768), "attn_out": (T, 768, 768), "ffn1": (T, 3072, 768), "ffn2": (T, 768, 3072)}.items():
+    shapes = {"qkv": (T, 2304, 768), "attn_out": (T, 768, 768), "ffn1": (T, 3072, 768), "ffn2": (T, 768, 3072)}
+    for name, (M, N, K) in shapes.items():
         x = torch.randn(M, K, device="cuda").bfloat16()
         w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        bias = torch.randn(N, device="cuda")
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        ms = timeit(lambda: ops.linear_fwd(x, w, None, out=out))
-        ms_t = timeit(lambda: torch.matmul(x, w.t(), out=out))
-        fl = 2.0 * M * N * K
-        # dgrad / wgrad
+        out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        res_in = torch.randn(M, N, device="cuda").bfloat16()
         dy = torch.randn(M, N, device="cuda").bfloat16()
         dx = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
-        ms_d = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx))
         dw = torch.zeros(N, K, device="cuda")
-        ms_w = timeit(lambda: ops.linear_wgrad(dy, x, dw))
-        r = dict(name=name, M=M, N=N, K=K, fwd_ms=ms, fwd_tflops=fl / ms / 1e9, cublas_ms=ms_t, cublas_tflops=fl / ms_t / 1e9,
-                 dgrad_ms=ms_d, dgrad_tflops=fl / ms_d / 1e9, wgrad_ms=ms_w, wgrad_tflops=fl / ms_w / 1e9)
-        print(json.dumps(r)); res.append(r)
+        fl = 2.0 * M * N * K
+        ms_t = timeit(lambda: torch.matmul(x, w.t(), out=out))
+        r = dict(name=name, M=M, N=N, K=K, cublas_tflops=round(fl / ms_t / 1e9, 1))
+        for impl in impls:
+            ops.set_gemm_impl(impl)
+            t = {}
+            t["fwd"] = timeit(lambda: ops.linear_fwd(x, w, None, out=out))
+            t["fwd_bias_gelu"] = timeit(lambda: ops.linear_fwd(x, w, bias, out=out, mode=Lb.EPI_GELU, out2=out2))
+            t["fwd_resid_drop"] = timeit(lambda: ops.linear_fwd(x, w, bias, out=out, mode=Lb.EPI_RESID, aux=res_in,
+                                                                 p_drop=0.1, seed=5))
+            t["dgrad"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx))
+            t["wgrad"] = timeit(lambda: ops.linear_wgrad(dy, x, dw))
+            for k, v in t.items():
+                r["%s_%s_tflops" % (impl, k)] = round(fl / v / 1e9, 1)
+        ops.set_gemm_impl("auto")
+        print(json.dumps(r), flush=True)
+        res.append(r)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_gemm.json", "w"), indent=1)
+
 
 if __name__ == "__main__":
     main()
