@@ -127,17 +127,17 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 // used by the bf16 tensor-core epilogues (results are rounded to bf16, eps 3.9e-3); the fp32 parity path
 // keeps erff.  `e_out` = exp(-x^2/2), shared with the Gaussian pdf of GELU'.
 __device__ __forceinline__ float normal_cdf_fast(float x, float& e_out) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  // t = 1 / (1 + p |x|/sqrt2);  e = exp(-x^2/2);  0.5 erfc(|x|/sqrt2) = t (c1 + t (c2 + ...)) e  (c_i = a_i / 2)
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * -0.72134752044448170f) * x));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
   e_out = e;
-  const float half_erfc = 0.5f * p * e;             // 0.5 * erfc(|x|/sqrt2)
-  return x >= 0.f ? 1.f - half_erfc : half_erfc;
+  const float h = (p * t) * e;
+  return x >= 0.f ? 1.f - h : h;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float e;
@@ -152,16 +152,14 @@ __device__ __forceinline__ float dgelu_fast(float x) {
 // ---- dropout: counter-based hash RNG, recomputed (never stored) in backward ----------------------
 // keep(seed, stream, idx) is a pure function; `stream` separates the dropout sites of one step.
 __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
-  // 3 multiply / xor-shift rounds over (idx, seed): ~11 integer ops per element (the epilogues and the
-  // attention softmax are issue-bound, so the mask must be cheap); plenty for a Bernoulli mask
+  // two multiply rounds over (idx, seed) with a xor-shift in between: 8 integer ops per element (the GEMM
+  // epilogues and the attention softmax are issue-bound, so the mask must be cheap).  Only the HIGH bits
+  // matter (the caller compares against a threshold), and those are fully mixed by the second multiply.
   const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
   const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
   uint32_t h = (lo ^ s0) * 0x9E3779B1u;
   h ^= h >> 15;
   h = (h ^ (hi * 0x85EBCA77u + s1)) * 0xC2B2AE3Du;
-  h ^= h >> 13;
-  h *= 0x27D4EB2Fu;
-  h ^= h >> 16;
   return h;
 }
 // threshold = round(p * 2^32) (clamped); element is KEPT iff bits >= threshold

@@ -23,25 +23,52 @@ struct StagedEpi {
   static constexpr int kBytesPerWarp = (kOutBufs + kAuxBufs) * kEpiBoxBytes;
 };
 
+// dropout keep-mask bits for 32 consecutive elements starting at 64-bit index idx0 (same function as
+// dropout_keep(seed, idx0 + j, thr) of common.cuh, with the seed / high-word terms hoisted out of the loop)
+__device__ __forceinline__ uint32_t dropout_mask32(unsigned long long seed, unsigned long long idx0, uint32_t thr) {
+  const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t lo0 = static_cast<uint32_t>(idx0), hi0 = static_cast<uint32_t>(idx0 >> 32);
+  uint32_t keep = 0;
+  if (lo0 <= 0xFFFFFFFFu - 31u) {
+    const uint32_t hterm = hi0 * 0x85EBCA77u + s1;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t h = ((lo0 + j) ^ s0) * 0x9E3779B1u;
+      h ^= h >> 15;
+      h = (h ^ hterm) * 0xC2B2AE3Du;
+      keep |= (h >= thr ? 1u : 0u) << j;
+    }
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) keep |= (dropout_keep(seed, idx0 + j, thr) ? 1u : 0u) << j;
+  }
+  return keep;
+}
+
 // math of one 32-column chunk of one row: acc (TMEM registers) -> packed bf16 pairs.
 // aux4: the thread's 4 x 16-byte pieces (32 bf16) of the auxiliary operand, already in registers.
-template <int MODE>
+// FULL: all 32 columns are < N (no per-element guards on the bias loads).
+template <int MODE, bool FULL>
 __device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t (&r)[32], const uint4 (&aux4)[4],
                                               int row, int col0, int N, uint32_t (&outp)[16], uint32_t (&prep)[16]) {
   constexpr bool needs_aux = StagedEpi<MODE>::kAux;
-  const bool full = (col0 + 32 <= N);
+  uint32_t keep = 0xFFFFFFFFu;
+  if (MODE == MTVAF_EPI_RESID && ep.drop_threshold)
+    keep = dropout_mask32(ep.seed, (unsigned long long)row * (unsigned long long)N + col0, ep.drop_threshold);
+  const bool has_bias = ep.bias != nullptr;
+  const float alpha = ep.alpha;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float v[8], a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-    if (ep.alpha != 1.f) {
+    if (alpha != 1.f) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= ep.alpha;
+      for (int j = 0; j < 8; ++j) v[j] *= alpha;
     }
-    if (ep.bias) {
+    if (has_bias) {
       const int c = col0 + g * 8;
-      if (full) {
+      if (FULL) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + 4));
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
@@ -60,9 +87,14 @@ __device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t 
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float pre = v[j];
-      o[j] = epi_math<MODE, true>(ep, v[j], needs_aux ? a[j] : 0.f, row, col0 + g * 8 + j, N, pre);
-      v[j] = pre;
+      const float x = v[j];
+      if (MODE == MTVAF_EPI_GELU) o[j] = gelu_fast(x);
+      else if (MODE == MTVAF_EPI_TANH) o[j] = tanhf(x);
+      else if (MODE == MTVAF_EPI_RESID)
+        o[j] = ((keep >> (g * 8 + j)) & 1u) ? fmaf(x, ep.drop_scale, a[j]) : a[j];
+      else if (MODE == MTVAF_EPI_MUL_DGELU) o[j] = x * dgelu_fast(a[j]);
+      else if (MODE == MTVAF_EPI_MUL_DTANH) o[j] = x * (1.f - a[j] * a[j]);
+      else o[j] = x;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) outp[g * 4 + j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);

@@ -283,7 +283,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             tmem_ld_wait();
             uint32_t o[16], p[16];
-            epi_compute32<EPI>(ep, r, aux4, row, col0 + sub * 32, N, o, p);
+            if (col0 + 64 <= N) epi_compute32<EPI, true>(ep, r, aux4, row, col0 + sub * 32, N, o, p);
+            else epi_compute32<EPI, false>(ep, r, aux4, row, col0 + sub * 32, N, o, p);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint32_t off = box_piece_off(lane, sub * 4 + g);
