@@ -121,10 +121,14 @@ int mtvaf_embed_ln_bwd(const void* dout, int dtype, const int64_t* input_ids, co
  * (fused into the GEMM epilogue MTVAF_EPI_RESID). */
 int mtvaf_layernorm_fwd(const void* z, void* y, const float* gamma, const float* beta, float eps, int rows, int H,
                         int dtype, float* mean, float* rstd, void* stream);
-/* dz = LN backward (dtype); d_gamma/d_beta accumulated with fp32 atomics.  If `dres_add` is non-NULL
- * it is added to the result (gradient arriving through the residual branch of the NEXT op). */
+/* dz = LN backward (dtype); d_gamma/d_beta accumulated with fp32 atomics.  Fused tail of the backward of
+ * `LN(dropout(dense(x)) + residual)`: when p_drop > 0, `dd` (same dtype/shape as dz, required) receives
+ * dropout_mask(seed, m*H+n) * dz / (1-p) -- the gradient entering the dense layer's GEMMs, same mask as the
+ * forward MTVAF_EPI_RESID epilogue; when `d_bias` is non-NULL, d_bias[n] += sum_m dd[m,n] (dd == dz if p == 0),
+ * i.e. the dense layer's bias gradient, so no separate dropout / column-sum pass is needed. */
 int mtvaf_layernorm_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
-                        int rows, int H, int dtype, void* dz, float* d_gamma, float* d_beta, void* stream);
+                        int rows, int H, int dtype, void* dz, float* d_gamma, float* d_beta, void* dd,
+                        float* d_bias, float p_drop, uint64_t seed, void* stream);
 
 /* ---- prefix ("fusion") attention: RobertaSelfAttention.forward modeling_roberta.py:218-278 ---- */
 /* qkv: [B*L, 3*nh*d] (Q | K | V column blocks, the fused QKV projection output), row stride ld_qkv.
@@ -202,9 +206,11 @@ int mtvaf_combine_loss(const float* crf_nll_sum, int B, const float* prob_loss, 
                        void* stream);
 
 /* ---- optimizer: torch.optim.AdamW as configured in modules/train.py:887-926 ------------------- */
-int mtvaf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+/* zero_grad != 0 clears `grad` in the same pass (replaces optimizer.zero_grad()); bf16_copy (optional) receives
+ * the updated weights rounded to bf16 (the tensor-core GEMM operands). */
+int mtvaf_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                     void* bf16_copy, void* stream);
+                     void* bf16_copy, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,16 @@ template <typename T>
 struct Vec8;
 template <>
 struct Vec8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  static __device__ __forceinline__ void cvt(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
     float4 a = *reinterpret_cast<const float4*>(p);
     float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -69,6 +79,12 @@ struct Vec8<float> {
 };
 template <>
 struct Vec8<__nv_bfloat16> {
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void cvt(const Raw& u, float (&v)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);

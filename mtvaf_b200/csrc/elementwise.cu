@@ -66,6 +66,51 @@ __global__ void colsum_kernel(const T* __restrict__ dy, long long ld, int M, int
   }
 }
 
+// vector form: a warp covers 256 columns of one row with 16-byte (bf16) / 32-byte (fp32) loads, 8 warps take
+// interleaved rows, 4 rows in flight per thread; used whenever N % 8 == 0 and the rows are 16-byte aligned
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ dy, long long ld, int M, int N, int rows_per_block, float* __restrict__ db) {
+  __shared__ float red[8][256 + 8];
+  using V = Vec8<T>;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + tx * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < N) {
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      typename V::Raw v0 = V::load_raw(dy + (long long)r * ld + c);
+      typename V::Raw v1 = V::load_raw(dy + (long long)(r + 8) * ld + c);
+      typename V::Raw v2 = V::load_raw(dy + (long long)(r + 16) * ld + c);
+      typename V::Raw v3 = V::load_raw(dy + (long long)(r + 24) * ld + c);
+      float f0[8], f1[8], f2[8], f3[8];
+      V::cvt(v0, f0); V::cvt(v1, f1); V::cvt(v2, f2); V::cvt(v3, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < r1; r += 8) {
+      float f0[8];
+      V::load(dy + (long long)r * ld + c, f0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f0[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < N) atomicAdd(db + cc, s);
+  }
+}
+
 // ------------------------------------------------------------------ 4-way means of the prompt
 // x: [rows, 4, W].  mode 0: y[row, w] = mean_r x[row, r, w]                 (bert_model.py:550)
 //                   mode 1: y[row, r*S + c] = mean_i x[row, r, i*S + c], S = W/4   (bert_model.py:567)
@@ -170,21 +215,64 @@ __global__ void combine_loss_kernel(const float* crf_nll_sum, float inv_b, const
 }
 
 // ------------------------------------------------------------------ AdamW (torch.optim.AdamW semantics)
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float gscale, __nv_bfloat16* __restrict__ bf) {
+__device__ __forceinline__ void adamw_one(float& w, float g, float& m, float& v, float lr, float b1, float b2,
+                                          float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  const float grad = g * gscale;
+  w *= (1.f - lr * wd);
+  m = b1 * m + (1.f - b1) * grad;
+  v = b2 * v + (1.f - b2) * grad * grad;
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  w -= (lr / bc1) * (m / denom);
+}
+// 16-byte vector form (n4 = n / 4 quads; the caller guarantees 16-byte aligned bases); optionally refreshes the
+// bf16 weight shadow and clears the gradient in the same pass (zero_grad), so a training step needs no
+// separate cast or memset over the 125 M parameters
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+             __nv_bfloat16* __restrict__ bf, int zero_grad) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 w4 = reinterpret_cast<float4*>(p)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i];
+    float4 v4 = reinterpret_cast<float4*>(v)[i];
+    adamw_one(w4.x, g4.x, m4.x, v4.x, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    adamw_one(w4.y, g4.y, m4.y, v4.y, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    adamw_one(w4.z, g4.z, m4.z, v4.z, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    adamw_one(w4.w, g4.w, m4.w, v4.w, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    reinterpret_cast<float4*>(p)[i] = w4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bf) {
+      uint2 u;
+      u.x = pack_bf16x2(w4.x, w4.y);
+      u.y = pack_bf16x2(w4.z, w4.w);
+      reinterpret_cast<uint2*>(bf)[i] = u;
+    }
+  }
+  // scalar tail (n % 4 elements)
+  const long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float w = p[t], mi = m[t], vi = v[t];
+    adamw_one(w, g[t], mi, vi, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    p[t] = w; m[t] = mi; v[t] = vi;
+    if (zero_grad) g[t] = 0.f;
+    if (bf) bf[t] = __float2bfloat16_rn(w);
+  }
+}
+__global__ void adamw_scalar_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                    float wd, float bc1, float bc2_sqrt, float gscale, __nv_bfloat16* __restrict__ bf,
+                                    int zero_grad) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float grad = g[i] * gscale;
-    float w = p[i];
-    w *= (1.f - lr * wd);
-    const float mi = b1 * m[i] + (1.f - b1) * grad;
-    const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    w -= (lr / bc1) * (mi / denom);
-    p[i] = w;
+    float w = p[i], mi = m[i], vi = v[i];
+    adamw_one(w, g[i], mi, vi, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    p[i] = w; m[i] = mi; v[i] = vi;
+    if (zero_grad) g[i] = 0.f;
     if (bf) bf[i] = __float2bfloat16_rn(w);
   }
 }
@@ -249,17 +337,29 @@ extern "C" int mtvaf_add_inplace(void* dst, int dst_dtype, const void* src, int 
 
 extern "C" int mtvaf_colsum(const void* dy, int64_t ld, int dtype, int M, int N, float* db, void* stream) {
   MTVAF_REQUIRE(dy && db && M > 0 && N > 0, "colsum: bad argument");
-  const int col_blocks = (N + 63) / 64;
-  int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int esz = dtype == MTVAF_BF16 ? 2 : 4;
+  const bool vec = N % 8 == 0 && (ld * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(dy) % 16 == 0;
+  const int cols_per_block = vec ? 256 : 64;
+  const int col_blocks = (N + cols_per_block - 1) / cols_per_block;
+  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
   int rows_per_block = (M + row_blocks - 1) / row_blocks;
-  rows_per_block = ((rows_per_block + 7) / 8) * 8;
-  if (rows_per_block < 8) rows_per_block = 8;
+  const int gran = vec ? 32 : 8;
+  rows_per_block = ((rows_per_block + gran - 1) / gran) * gran;
+  if (rows_per_block < gran) rows_per_block = gran;
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
   dim3 grid(col_blocks, row_blocks);
-  if (dtype == MTVAF_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, ld, M, N, rows_per_block, db);
-  else
-    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, ld, M, N, rows_per_block, db);
+  if (vec) {
+    if (dtype == MTVAF_BF16)
+      colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, ld, M, N, rows_per_block, db);
+    else
+      colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, ld, M, N, rows_per_block, db);
+  } else {
+    if (dtype == MTVAF_BF16)
+      colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, ld, M, N, rows_per_block, db);
+    else
+      colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, ld, M, N, rows_per_block, db);
+  }
   MTVAF_LAUNCH_CHECK();
   return 0;
 }
@@ -325,16 +425,24 @@ extern "C" int mtvaf_combine_loss(const float* crf_nll_sum, int B, const float* 
   return 0;
 }
 
-extern "C" int mtvaf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+extern "C" int mtvaf_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                                float grad_scale, void* bf16_copy, void* stream) {
+                                float grad_scale, void* bf16_copy, int zero_grad, void* stream) {
   if (n <= 0) return 0;
   MTVAF_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "adamw: bad argument");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  adamw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                   beta2, eps, weight_decay, bc1, sqrtf(bc2),
-                                                                   grad_scale, (__nv_bfloat16*)bf16_copy);
+  auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
+  const bool vec = al(param, 16) && al(grad, 16) && al(exp_avg, 16) && al(exp_avg_sq, 16) &&
+                   (!bf16_copy || al(bf16_copy, 8));
+  if (vec)
+    adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale,
+        (__nv_bfloat16*)bf16_copy, zero_grad);
+  else
+    adamw_scalar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale,
+        (__nv_bfloat16*)bf16_copy, zero_grad);
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -75,42 +75,64 @@ layernorm_fwd_kernel(const T* __restrict__ z, T* __restrict__ y, const float* __
 }
 
 // dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (z - mean) * rstd
-// d_gamma += sum_rows dy * xhat, d_beta += sum_rows dy (per-warp register partials -> smem -> atomics)
-template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// d_gamma += sum_rows dy * xhat, d_beta += sum_rows dy (per-warp register partials -> smem -> atomics).
+// Fused tail of the backward of `LN(dropout(dense) + residual)` (modeling_roberta.py:296-298,379-381):
+//   dd = dropout_mask o dz / (1-p)  (the gradient entering the dense GEMMs; written when p > 0),
+//   d_bias += sum_rows dd           (bias gradient of that dense layer),
+// so the separate dropout and column-sum passes over [T,H] disappear.
+// NV = ceil(H / 256) vectors of 8 elements per lane; the next row's loads are issued before the current
+// row's reductions (raw 16-byte vectors held in registers) to keep enough bytes in flight per SM.
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, (NV <= 3 && sizeof(T) == 2) ? 3 : 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int rows, int H,
-                     T* __restrict__ dz, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-  __shared__ float sg[LN_WARPS][LN_MAX_VEC * 32 * 8 / 4];   // reused in two halves below
+                     T* __restrict__ dz, T* __restrict__ dd, float* __restrict__ d_gamma, float* __restrict__ d_beta,
+                     float* __restrict__ d_bias, uint32_t drop_thr, float drop_scale, unsigned long long seed) {
+  __shared__ float red[LN_WARPS * 256];
+  using V = Vec8<T>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ag[LN_MAX_VEC][8], ab[LN_MAX_VEC][8];
+  float ag[NV][8], ab[NV][8], ac[NV][8];
 #pragma unroll
-  for (int v = 0; v < LN_MAX_VEC; ++v)
+  for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[v][j] = 0.f; ab[v][j] = 0.f; }
-  float gm[LN_MAX_VEC][8];
+    for (int j = 0; j < 8; ++j) { ag[v][j] = 0.f; ab[v][j] = 0.f; ac[v][j] = 0.f; }
+  const int stride = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + warp;
+  typename V::Raw rz[NV], rg[NV];
+  if (row < rows) {
 #pragma unroll
-  for (int v = 0; v < LN_MAX_VEC; ++v) {
-    const int c = (v * 32 + lane) * 8;
-    if (c < H) Vec8<float>::load(gamma + c, gm[v]);
+    for (int v = 0; v < NV; ++v) {
+      const int c = (v * 32 + lane) * 8;
+      if (c < H) { rz[v] = V::load_raw(z + (long long)row * H + c); rg[v] = V::load_raw(dy + (long long)row * H + c); }
+    }
   }
-  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
-    float x[LN_MAX_VEC][8], g[LN_MAX_VEC][8];
-    ln_load_row<T>(z + (long long)row * H, H, lane, x);
-    ln_load_row<T>(dy + (long long)row * H, H, lane, g);
+  for (; row < rows; row += stride) {
+    float x[NV][8], g[NV][8];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { V::cvt(rz[v], x[v]); V::cvt(rg[v], g[v]); }
     const float mean = mean_in[row], rstd = rstd_in[row];
+    const int nrow = row + stride;
+    if (nrow < rows) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = (v * 32 + lane) * 8;
+        if (c < H) { rz[v] = V::load_raw(z + (long long)nrow * H + c); rg[v] = V::load_raw(dy + (long long)nrow * H + c); }
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < LN_MAX_VEC; ++v) {
+    for (int v = 0; v < NV; ++v) {
       const int c = (v * 32 + lane) * 8;
       if (c < H) {
+        float gm[8];
+        Vec8<float>::load(gamma + c, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (x[v][j] - mean) * rstd;
           const float d = g[v][j];
           ag[v][j] += d * xh;
           ab[v][j] += d;
-          const float gg = d * gm[v][j];
+          const float gg = d * gm[j];
           x[v][j] = xh;
           g[v][j] = gg;
           s1 += gg;
@@ -121,31 +143,41 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const fl
     s1 = warp_sum(s1) / (float)H;
     s2 = warp_sum(s2) / (float)H;
 #pragma unroll
-    for (int v = 0; v < LN_MAX_VEC; ++v) {
+    for (int v = 0; v < NV; ++v) {
       const int c = (v * 32 + lane) * 8;
       if (c < H) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[v][j] - s1 - x[v][j] * s2);
-        Vec8<T>::store(dz + (long long)row * H + c, o);
+        V::store(dz + (long long)row * H + c, o);
+        if (drop_thr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = dropout_keep(seed, (unsigned long long)row * H + c + j, drop_thr) ? o[j] * drop_scale : 0.f;
+          V::store(dd + (long long)row * H + c, o);
+        }
+        if (d_bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ac[v][j] += o[j];
+        }
       }
     }
   }
   // reduce the per-warp parameter-gradient partials across the block, then one atomic per column
-  float* red = &sg[0][0];   // LN_WARPS * 256 floats
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (d_bias ? 3 : 2); ++pass) {
+    float* dst = pass == 0 ? d_gamma : pass == 1 ? d_beta : d_bias;
 #pragma unroll
-    for (int v = 0; v < LN_MAX_VEC; ++v) {
+    for (int v = 0; v < NV; ++v) {
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp * 256 + lane * 8 + j] = pass == 0 ? ag[v][j] : ab[v][j];
+      for (int j = 0; j < 8; ++j) red[warp * 256 + lane * 8 + j] = pass == 0 ? ag[v][j] : pass == 1 ? ab[v][j] : ac[v][j];
       __syncthreads();
       for (int i = threadIdx.x; i < 256; i += LN_WARPS * 32) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < LN_WARPS; ++w) s += red[w * 256 + i];
         const int c = v * 256 + i;
-        if (c < H) atomicAdd((pass == 0 ? d_gamma : d_beta) + c, s);
+        if (c < H) atomicAdd(dst + c, s);
       }
     }
   }
@@ -222,42 +254,77 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// Backward of the embedding sum + LayerNorm.  The three scatter-adds are the hard part: every token adds a
+// full row to word[id], pos[pid] and type[tt], and on real batches most tokens collide (all token types are 0,
+// each position id occurs once per sequence, ~3/4 of the ids are the padding token), so per-element atomics
+// serialise in L2.  Each warp therefore walks the tokens in POSITION-major order (l outer, b inner: the
+// position row and the type row stay the same for a whole run) and keeps register accumulators
+//   ade : sum of dE over the current run of equal (token type, position id)   -> flushed to both tables
+//   aw  : sum of dE over the rows whose id equals the batch's hot id (the padding token) -> flushed once
+// next to the d_gamma / d_beta partials; only rows with other ids scatter directly (16-byte vector atomics).
+__device__ __forceinline__ void red_add_v8(float* p, const float (&v)[8]) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 embed_ln_bwd_kernel(const T* __restrict__ dout, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
                     const int64_t* __restrict__ pos, const float* __restrict__ word, const float* __restrict__ pemb,
                     const float* __restrict__ temb, const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                    const float* __restrict__ rstd_in, int rows, int H, int word_pad, int pos_pad,
+                    const float* __restrict__ rstd_in, int B, int L, int H, int word_pad, int pos_pad,
                     float* __restrict__ d_word, float* __restrict__ d_pos, float* __restrict__ d_type,
                     float* __restrict__ d_gamma, float* __restrict__ d_beta, uint32_t drop_thr, float drop_scale,
                     unsigned long long seed) {
   __shared__ float red[LN_WARPS * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ag[LN_MAX_VEC][8], ab[LN_MAX_VEC][8], gm[LN_MAX_VEC][8];
+  const int rows = B * L;
+  float ag[NV][8], ab[NV][8], ade[NV][8], aw[NV][8];
 #pragma unroll
-  for (int v = 0; v < LN_MAX_VEC; ++v) {
-    const int c = (v * 32 + lane) * 8;
+  for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[v][j] = 0.f; ab[v][j] = 0.f; }
-    if (c < H) Vec8<float>::load(gamma + c, gm[v]);
-  }
-  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    for (int j = 0; j < 8; ++j) { ag[v][j] = 0.f; ab[v][j] = 0.f; ade[v][j] = 0.f; aw[v][j] = 0.f; }
+  const long long hot = ids[rows - 1];            // the last token of the batch: the padding id if there is any padding
+  long long run_tt = -1, run_ps = -1;
+  auto flush_run = [&]() {
+    if (run_tt < 0) return;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = (v * 32 + lane) * 8;
+      if (c < H) {
+        red_add_v8(d_type + run_tt * (long long)H + c, ade[v]);
+        if (run_ps != pos_pad) red_add_v8(d_pos + run_ps * (long long)H + c, ade[v]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ade[v][j] = 0.f;
+      }
+    }
+  };
+  // contiguous chunk of the position-major token order per warp
+  const int n_warps = gridDim.x * LN_WARPS;
+  const int chunk = (rows + n_warps - 1) / n_warps;
+  const int j0 = (blockIdx.x * LN_WARPS + warp) * chunk;
+  const int j1 = min(rows, j0 + chunk);
+  for (int jj = j0; jj < j1; ++jj) {
+    const int l = jj / B, bb = jj - l * B;
+    const int row = bb * L + l;
     const long long id = ids[row], ps = pos[row], tt = tts[row];
+    if (tt != run_tt || ps != run_ps) { flush_run(); run_tt = tt; run_ps = ps; }
     const float* w = word + id * (long long)H;
     const float* p = pemb + ps * (long long)H;
     const float* t = temb + tt * (long long)H;
-    float x[LN_MAX_VEC][8], g[LN_MAX_VEC][8];
-    ln_load_row<T>(dout + (long long)row * H, H, lane, g);
+    float x[NV][8], g[NV][8];
     const float mean = mean_in[row], rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < LN_MAX_VEC; ++v) {
+    for (int v = 0; v < NV; ++v) {
       const int c = (v * 32 + lane) * 8;
       if (c < H) {
-        float a[8], b[8], d[8];
+        float a[8], b[8], d[8], gm[8];
+        Vec8<T>::load(dout + (long long)row * H + c, g[v]);
         Vec8<float>::load(w + c, a);
         Vec8<float>::load(t + c, b);
         Vec8<float>::load(p + c, d);
+        Vec8<float>::load(gamma + c, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float dd = g[v][j];
@@ -265,7 +332,7 @@ embed_ln_bwd_kernel(const T* __restrict__ dout, const int64_t* __restrict__ ids,
           const float xh = (((a[j] + b[j]) + d[j]) - mean) * rstd;
           ag[v][j] += dd * xh;
           ab[v][j] += dd;
-          const float gg = dd * gm[v][j];
+          const float gg = dd * gm[j];
           x[v][j] = xh;
           g[v][j] = gg;
           s1 += gg;
@@ -275,23 +342,33 @@ embed_ln_bwd_kernel(const T* __restrict__ dout, const int64_t* __restrict__ ids,
     }
     s1 = warp_sum(s1) / (float)H;
     s2 = warp_sum(s2) / (float)H;
+    const bool is_hot = id == hot;
 #pragma unroll
-    for (int v = 0; v < LN_MAX_VEC; ++v) {
+    for (int v = 0; v < NV; ++v) {
       const int c = (v * 32 + lane) * 8;
       if (c < H) {
+        float de[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float de = rstd * (g[v][j] - s1 - x[v][j] * s2);
-          if (id != word_pad) atomicAdd(d_word + id * (long long)H + c + j, de);
-          if (ps != pos_pad) atomicAdd(d_pos + ps * (long long)H + c + j, de);
-          atomicAdd(d_type + tt * (long long)H + c + j, de);
+          de[j] = rstd * (g[v][j] - s1 - x[v][j] * s2);
+          ade[v][j] += de[j];
+          if (is_hot) aw[v][j] += de[j];
         }
+        if (!is_hot && id != word_pad) red_add_v8(d_word + id * (long long)H + c, de);
       }
+    }
+  }
+  flush_run();
+  if (hot != word_pad && j1 > j0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = (v * 32 + lane) * 8;
+      if (c < H) red_add_v8(d_word + hot * (long long)H + c, aw[v]);
     }
   }
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int v = 0; v < LN_MAX_VEC; ++v) {
+    for (int v = 0; v < NV; ++v) {
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < 8; ++j) red[warp * 256 + lane * 8 + j] = pass == 0 ? ag[v][j] : ab[v][j];
@@ -338,23 +415,40 @@ extern "C" int mtvaf_layernorm_fwd(const void* z, void* y, const float* gamma, c
   return 0;
 }
 
-extern "C" int mtvaf_layernorm_bwd(const void* dy, const void* z, const float* gamma, const float* mean,
-                                   const float* rstd, int rows, int H, int dtype, void* dz, float* d_gamma,
-                                   float* d_beta, void* stream) {
-  MTVAF_REQUIRE(dy && z && gamma && mean && rstd && dz && d_gamma && d_beta && rows > 0, "layernorm_bwd: bad argument");
-  MTVAF_REQUIRE(H % 8 == 0 && H <= LN_MAX_VEC * 256, "layernorm: H=%d unsupported", H);
+template <typename T>
+static int launch_ln_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+                         int rows, int H, void* dz, void* dd, float* d_gamma, float* d_beta, float* d_bias,
+                         uint32_t thr, float scale, uint64_t seed, cudaStream_t st) {
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int cap = sm_count() * 4;
+  const int nv = (H + 255) / 256;
+  const int cap = sm_count() * ((nv <= 3 && sizeof(T) == 2) ? 3 : 2);   // resident blocks per SM (register-limited)
   if (grid > cap) grid = cap;
-  if (dtype == MTVAF_BF16)
-    layernorm_bwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)z, gamma, mean, rstd, rows, H, (__nv_bfloat16*)dz, d_gamma,
-        d_beta);
-  else
-    layernorm_bwd_kernel<float><<<grid, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        (const float*)dy, (const float*)z, gamma, mean, rstd, rows, H, (float*)dz, d_gamma, d_beta);
+#define MTVAF_LN_BWD(NV_)                                                                                          \
+  layernorm_bwd_kernel<T, NV_><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)z, gamma, mean, rstd, rows, H, \
+                                                              (T*)dz, (T*)dd, d_gamma, d_beta, d_bias, thr, scale, seed)
+  if (nv == 1) MTVAF_LN_BWD(1);
+  else if (nv == 2) MTVAF_LN_BWD(2);
+  else if (nv == 3) MTVAF_LN_BWD(3);
+  else MTVAF_LN_BWD(4);
+#undef MTVAF_LN_BWD
   MTVAF_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mtvaf_layernorm_bwd(const void* dy, const void* z, const float* gamma, const float* mean,
+                                   const float* rstd, int rows, int H, int dtype, void* dz, float* d_gamma,
+                                   float* d_beta, void* dd, float* d_bias, float p_drop, uint64_t seed,
+                                   void* stream) {
+  MTVAF_REQUIRE(dy && z && gamma && mean && rstd && dz && d_gamma && d_beta && rows > 0, "layernorm_bwd: bad argument");
+  MTVAF_REQUIRE(H % 8 == 0 && H <= LN_MAX_VEC * 256, "layernorm: H=%d unsupported", H);
+  uint32_t thr; float scale;
+  if (int rc = drop_params(p_drop, &thr, &scale)) return rc;
+  MTVAF_REQUIRE(thr == 0 || dd != nullptr, "layernorm_bwd: p_drop > 0 needs the `dd` output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTVAF_BF16)
+    return launch_ln_bwd<__nv_bfloat16>(dy, z, gamma, mean, rstd, rows, H, dz, dd, d_gamma, d_beta, d_bias, thr,
+                                        scale, seed, st);
+  return launch_ln_bwd<float>(dy, z, gamma, mean, rstd, rows, H, dz, dd, d_gamma, d_beta, d_bias, thr, scale, seed, st);
 }
 
 extern "C" int mtvaf_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const float* word_emb,
@@ -400,19 +494,26 @@ extern "C" int mtvaf_embed_ln_bwd(const void* dout, int dtype, const int64_t* in
   uint32_t thr; float scale;
   if (int rc = drop_params(p_drop, &thr, &scale)) return rc;
   const int rows = B * L;
-  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int cap = sm_count() * 4;
+  int grid = (rows + LN_WARPS * 8 - 1) / (LN_WARPS * 8);      // >= 8 tokens per warp so runs can aggregate
+  const int cap = sm_count() * 2;
   if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
   // nn.Embedding(padding_idx): word table always; position table only for roberta (modeling_roberta.py:98-100)
   const int word_pad = pad_idx, pos_pad = (kind == 0) ? pad_idx : -1;
-  if (dtype == MTVAF_BF16)
-    embed_ln_bwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dout, input_ids, token_type_ids, position_ids, word_emb, pos_emb, type_emb, gamma, mean,
-        rstd, rows, H, word_pad, pos_pad, d_word, d_pos, d_type, d_gamma, d_beta, thr, scale, seed);
-  else
-    embed_ln_bwd_kernel<float><<<grid, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        (const float*)dout, input_ids, token_type_ids, position_ids, word_emb, pos_emb, type_emb, gamma, mean, rstd,
-        rows, H, word_pad, pos_pad, d_word, d_pos, d_type, d_gamma, d_beta, thr, scale, seed);
+  const int nv = (H + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MTVAF_EMB_BWD(T_, NV_)                                                                                      \
+  embed_ln_bwd_kernel<T_, NV_><<<grid, LN_WARPS * 32, 0, st>>>((const T_*)dout, input_ids, token_type_ids,           \
+      position_ids, word_emb, pos_emb, type_emb, gamma, mean, rstd, B, L, H, word_pad, pos_pad, d_word, d_pos,      \
+      d_type, d_gamma, d_beta, thr, scale, seed)
+  if (dtype == MTVAF_BF16) {
+    if (nv == 1) MTVAF_EMB_BWD(__nv_bfloat16, 1); else if (nv == 2) MTVAF_EMB_BWD(__nv_bfloat16, 2);
+    else if (nv == 3) MTVAF_EMB_BWD(__nv_bfloat16, 3); else MTVAF_EMB_BWD(__nv_bfloat16, 4);
+  } else {
+    if (nv == 1) MTVAF_EMB_BWD(float, 1); else if (nv == 2) MTVAF_EMB_BWD(float, 2);
+    else if (nv == 3) MTVAF_EMB_BWD(float, 3); else MTVAF_EMB_BWD(float, 4);
+  }
+#undef MTVAF_EMB_BWD
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -326,23 +326,22 @@ class Engine:
             s = saved["layers"][i]
             ln = lambda nm: self.lname(i, nm)
             # ---- output block: y = LN(dropout(g W2^T + b2) + a)
-            dz2 = ops.layernorm_bwd(dy, s["z2"], f.w(ln("output.LayerNorm.weight")), s["m2"], s["r2"],
-                                    f.g(ln("output.LayerNorm.weight")), f.g(ln("output.LayerNorm.bias")))
-            dd2 = ops.dropout_apply(dz2, p_h, sd(16 * i + 4)) if p_h > 0 else dz2
+            dz2, dd2 = ops.layernorm_bwd(dy, s["z2"], f.w(ln("output.LayerNorm.weight")), s["m2"], s["r2"],
+                                         f.g(ln("output.LayerNorm.weight")), f.g(ln("output.LayerNorm.bias")),
+                                         d_bias=f.g(ln("output.dense.bias")), p_drop=p_h, seed=sd(16 * i + 4))
             ops.linear_wgrad(dd2, s["g"], f.g(ln("output.dense.weight")))
-            ops.colsum(dd2, f.g(ln("output.dense.bias")))
             dpre = ops.linear_dgrad(dd2, self.cw(ln("output.dense.weight")), mode=L.EPI_MUL_DGELU, aux=s["pre"])
             # ---- intermediate: g = gelu(a W1^T + b1)
             ops.linear_wgrad(dpre, s["a"], f.g(ln("intermediate.dense.weight")))
             ops.colsum(dpre, f.g(ln("intermediate.dense.bias")))
             da = ops.linear_dgrad(dpre, self.cw(ln("intermediate.dense.weight")), mode=L.EPI_RESID, aux=dz2)
             # ---- attention output block: a = LN(dropout(ctx Wo^T + bo) + x)
-            dz1 = ops.layernorm_bwd(da, s["z1"], f.w(ln("attention.output.LayerNorm.weight")), s["m1"], s["r1"],
-                                    f.g(ln("attention.output.LayerNorm.weight")),
-                                    f.g(ln("attention.output.LayerNorm.bias")))
-            dd1 = ops.dropout_apply(dz1, p_h, sd(16 * i + 3)) if p_h > 0 else dz1
+            dz1, dd1 = ops.layernorm_bwd(da, s["z1"], f.w(ln("attention.output.LayerNorm.weight")), s["m1"], s["r1"],
+                                         f.g(ln("attention.output.LayerNorm.weight")),
+                                         f.g(ln("attention.output.LayerNorm.bias")),
+                                         d_bias=f.g(ln("attention.output.dense.bias")), p_drop=p_h,
+                                         seed=sd(16 * i + 3))
             ops.linear_wgrad(dd1, s["ctx"], f.g(ln("attention.output.dense.weight")))
-            ops.colsum(dd1, f.g(ln("attention.output.dense.bias")))
             dctx = ops.linear_dgrad(dd1, self.cw(ln("attention.output.dense.weight")))
             # ---- attention core
             kp = vp = dkp = dvp = None
@@ -421,7 +420,10 @@ class Engine:
         # all 12 projectors in one skinny GEMM: [rows, 8H] x [n_layers*4, 8H]^T
         pw, pb = self._projector_pack()
         gs32 = ops.cast_f32(gs) if gs.dtype == BF16 else gs
-        gate_logits = ops.gemm(gs32, pw, M=rows, N=4 * c.n_layers, K=W8, bias=pb)
+        # skinny fp32 GEMM (N = 48): split K over the grid, partial sums accumulate onto the broadcast bias
+        gate_logits = pb.unsqueeze(0).repeat(rows, 1)
+        ops.gemm(gs32, pw, M=rows, N=4 * c.n_layers, K=W8, mode=L.EPI_ATOMIC_F32, out=gate_logits,
+                 splits=ops.skinny_splits(rows, 4 * c.n_layers, W8))
         kv, gates = ops.gate_fwd(guids, gate_logits, c.n_layers, n_img, B, H)
         saved.update(gs32=gs32, gate_logits=gate_logits, gates=gates)
         return kv, img_losses, (saved if save else None)

@@ -48,7 +48,7 @@ SIGNATURES = {
     "mtvaf_embed_ln_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                            _vp, _vp, _f, _u64, _vp],
     "mtvaf_layernorm_fwd": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp],
-    "mtvaf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mtvaf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _u64, _vp],
     "mtvaf_attention_fwd": [_vp, _i64, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _f, _u64, _vp],
     "mtvaf_set_attention_impl": [_i],
     "mtvaf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp,
@@ -64,7 +64,7 @@ SIGNATURES = {
     "mtvaf_crf_nll_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
     "mtvaf_crf_decode": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtvaf_combine_loss": [_vp, _i, _vp, _f, _i, _vp, _i, _f, _vp, _vp, _vp],
-    "mtvaf_adamw_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _vp],
+    "mtvaf_adamw_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i, _vp],
 }
 
 

@@ -144,6 +144,12 @@ def wgrad_splits(m_out: int, n_out: int, k: int, bf16: bool) -> int:
     return best
 
 
+def skinny_splits(M: int, N: int, K: int) -> int:
+    """split-K factor for the fp32 SIMT GEMM when the output has too few 128x128 tiles to fill the SMs."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    return max(1, min(K // 64, (2 * 148) // max(1, tiles)))
+
+
 def linear_wgrad(dy, x, dw: torch.Tensor, *, n_valid: Optional[int] = None):
     """dw[N,K] += dy^T x  (dy [M,N], x [M,K]); fp32 atomics into the gradient buffer."""
     M = dy.shape[0]
@@ -222,14 +228,17 @@ def layernorm_fwd(z, gamma, beta, eps, y=None):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, z, gamma, mean, rstd, d_gamma, d_beta, dz=None):
+def layernorm_bwd(dy, z, gamma, mean, rstd, d_gamma, d_beta, dz=None, d_bias=None, p_drop=0.0, seed=0):
+    """Returns (dz, dd): dd = dropout-masked dz (the gradient entering the preceding dense layer; dd is dz when
+    p_drop == 0); d_bias (optional) += column sums of dd."""
     rows, H = z.shape
     if dz is None:
         dz = torch.empty_like(z)
+    dd = torch.empty_like(z) if p_drop > 0 else None
     _check(_raw.mtvaf_layernorm_bwd(dy.data_ptr(), z.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                    rows, H, dt(z), dz.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), _stream()),
-           "layernorm_bwd")
-    return dz
+                                    rows, H, dt(z), dz.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), _p(dd),
+                                    _p(d_bias), p_drop, seed, _stream()), "layernorm_bwd")
+    return dz, (dd if dd is not None else dz)
 
 
 def embed_ln_fwd(ids, tts, word, pos, typ, gamma, beta, eps, kind, pad_idx, out_dtype, p_drop=0.0, seed=0):
@@ -382,6 +391,7 @@ def combine_loss(crf_nll_sum, B, prob_loss, beta, epoch, img_losses, alpha):
     return out, flag
 
 
-def adamw_step(param, grad, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0, bf16_copy=None):
+def adamw_step(param, grad, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0, bf16_copy=None, zero_grad=False):
     _check(_raw.mtvaf_adamw_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), lr, b1,
-                                 b2, eps, wd, step, grad_scale, _p(bf16_copy), _stream()), "adamw_step")
+                                 b2, eps, wd, step, grad_scale, _p(bf16_copy), int(zero_grad), _stream()),
+           "adamw_step")

@@ -66,7 +66,10 @@ class FlatAdamW:
             return s / max(1.0, float(self.warmup_steps))
         return max(0.0, (self.total_steps - s) / max(1.0, float(self.total_steps - self.warmup_steps)))
 
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, zero_grad: bool = False):
+        """One AdamW update of every range.  zero_grad=True clears the whole flat gradient buffer in the same
+        pass (the update kernels clear the ranges they own, one memset per gap of never-updated parameters),
+        replacing `optimizer.zero_grad()` / `model.zero_grad()` and its one-fill-per-parameter launches."""
         f = self.engine.flat
         scale = self.lr_scale()
         self.t += 1
@@ -76,9 +79,24 @@ class FlatAdamW:
             if bf and b <= f.cast_end:
                 shadow = f.Wb[a:b]
             ops.adamw_step(f.W[a:b], f.G[a:b], self.m[a:b], self.v[a:b], lr * scale, self.betas[0], self.betas[1],
-                           self.eps, wd, self.t, grad_scale, shadow)
+                           self.eps, wd, self.t, grad_scale, shadow, zero_grad)
+        if zero_grad:
+            for a, b in self._gaps():
+                f.G[a:b].zero_()
         if bf:
             f._wb_version = f.weights_version()     # shadow written by the fused kernel: still in sync
+
+    def _gaps(self):
+        if not hasattr(self, "_gap_list"):
+            gaps, pos = [], 0
+            for a, b, _, _ in sorted(self.ranges):
+                if a > pos:
+                    gaps.append((pos, a))
+                pos = max(pos, b)
+            if pos < self.engine.flat.total:
+                gaps.append((pos, self.engine.flat.total))
+            self._gap_list = gaps
+        return self._gap_list
 
     def zero_grad(self):
         self.engine.flat.G.zero_()

@@ -204,10 +204,36 @@ def test_layernorm_fwd_bwd(ops, dtype, H):
     dy = rnd(rows, H, seed=4, dtype=dtype)
     ref.backward(dy.float())
     dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
-    dz = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg, db)
+    dz, _ = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg, db)
     assert rel_err(dz, zf.grad) < tol
     assert rel_err(dg, gf.grad) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
     assert rel_err(db, bf_.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_layernorm_bwd_fused_dropout_and_bias_grad(ops, dtype, p_drop):
+    """The fused tail: dd = dropout-masked dz (same mask as ops.dropout_apply / the RESID epilogue) and
+    d_bias += column sums of dd."""
+    rows, H = 1500, 768
+    z = rnd(rows, H, seed=11, dtype=dtype)
+    gamma, beta = 1 + 0.1 * rnd(H, seed=12), 0.1 * rnd(H, seed=13)
+    _, mean, rstd = ops.layernorm_fwd(z, gamma, beta, 1e-5)
+    dy = rnd(rows, H, seed=14, dtype=dtype)
+    dg, db, dbias = (torch.zeros(H, device=DEV) for _ in range(3))
+    dg0, db0 = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dz_plain, same = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg0, db0)
+    assert same is dz_plain
+    dz, dd = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg, db, d_bias=dbias, p_drop=p_drop, seed=77)
+    assert torch.equal(dz, dz_plain) and torch.equal(dg, dg0) and torch.equal(db, db0)
+    if p_drop > 0:
+        keep = ops.dropout_apply(torch.ones(rows, H, device=DEV, dtype=dtype), p_drop, 77).float() > 0
+        want = torch.where(keep, dz.float() / (1 - p_drop), torch.zeros((), device=DEV))
+        assert rel_err(dd, want) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+        assert torch.equal(dd.float() != 0, keep & (dz.float() != 0))
+    else:
+        assert dd is dz
+    assert rel_err(dbias, dd.float().sum(0)) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
 
 
 @pytest.mark.parametrize("kind", ["roberta", "bert"])
@@ -493,3 +519,32 @@ def test_combine_loss_and_adamw(ops):
         opt.step()
         ops.adamw_step(p2, gr, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
     assert rel_err(p2, p.detach()) < 1e-6
+
+
+def test_adamw_vector_path_zero_grad_and_bf16_shadow(ops):
+    """16-byte vector AdamW with the fused gradient clear and bf16 weight shadow, odd length (scalar tail)."""
+    n = 4 * 1000 + 3
+    p = rnd(n, seed=1).requires_grad_()
+    p2 = p.detach().clone()
+    opt = torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    m, v = torch.zeros_like(p2), torch.zeros_like(p2)
+    shadow = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    for step in range(1, 4):
+        gr = rnd(n, seed=10 + step)
+        p.grad = gr.clone()
+        opt.step()
+        ops.adamw_step(p2, gr, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, bf16_copy=shadow, zero_grad=True)
+        assert float(gr.abs().max()) == 0.0
+    assert rel_err(p2, p.detach()) < 1e-6
+    assert torch.equal(shadow, p2.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,ld", [(1000, 768, 768), (4099, 3072, 3072), (333, 2304, 2304), (700, 2089, 2096),
+                                    (513, 11, 11), (64, 256, 512)])
+def test_colsum(ops, dtype, M, N, ld):
+    x = rnd(M, ld, seed=3, dtype=dtype)
+    db = torch.full((N,), 0.5, device=DEV)
+    ops.colsum(x, db, n_valid=N)
+    ref = x[:, :N].float().sum(0) + 0.5
+    assert rel_err(db, ref) < 1e-4
