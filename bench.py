@@ -200,8 +200,7 @@ def main():
         out.loss.backward()
         if sync is not None:
             sync.finish()
-        opt.step()
-        model.zero_grad(set_to_none=False)
+        opt.step(zero_grad=True)          # AdamW + gradient clear in one pass over the flat buffers
         return out.loss
 
     def barrier():

@@ -30,6 +30,8 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------------- */
 int mtvaf_abi_version(void);
 const char* mtvaf_last_error(void);
+/* number of CUDA kernels this library has launched so far in the process (statistics for benchmarks) */
+uint64_t mtvaf_launch_count(void);
 /* fills sm count and compute capability of the current device */
 int mtvaf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -133,9 +133,9 @@ attn_fwd_kernel(AttnArgs a, T* __restrict__ ctx, long long ld_ctx, float* __rest
       m[j] = mn;
       if (a.drop_thr) {
         const int q = q0 + warp * 4 + j;
-        const unsigned long long base = (((unsigned long long)b * a.nh + h) * a.L + q) * (unsigned long long)Lk + k0;
-        p0 = dropout_keep(a.seed, base + lane, a.drop_thr) ? p0 * a.drop_scale : 0.f;
-        p1 = dropout_keep(a.seed, base + lane + 32, a.drop_thr) ? p1 * a.drop_scale : 0.f;
+        const uint32_t rk = attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q);
+        p0 = attn_drop_keep(rk, k0 + lane, a.drop_thr) ? p0 * a.drop_scale : 0.f;
+        p1 = attn_drop_keep(rk, k0 + lane + 32, a.drop_thr) ? p1 * a.drop_scale : 0.f;
       }
       Ps[warp][j][lane] = p0;
       Ps[warp][j][lane + 32] = p1;
@@ -282,9 +282,9 @@ attn_bwd_dq_kernel(AttnArgs a, const T* __restrict__ dctx, long long ld_d, const
       float d0 = dp[j][0], d1 = dp[j][1];
       if (a.drop_thr) {
         const int q = q0 + warp * 4 + j;
-        const unsigned long long base = (((unsigned long long)b * a.nh + h) * a.L + q) * (unsigned long long)Lk + k0;
-        d0 = dropout_keep(a.seed, base + lane, a.drop_thr) ? d0 * a.drop_scale : 0.f;
-        d1 = dropout_keep(a.seed, base + lane + 32, a.drop_thr) ? d1 * a.drop_scale : 0.f;
+        const uint32_t rk = attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q);
+        d0 = attn_drop_keep(rk, k0 + lane, a.drop_thr) ? d0 * a.drop_scale : 0.f;
+        d1 = attn_drop_keep(rk, k0 + lane + 32, a.drop_thr) ? d1 * a.drop_scale : 0.f;
       }
       Ps[warp][j][lane] = p0 * (d0 - dsm[j]);
       Ps[warp][j][lane + 32] = p1 * (d1 - dsm[j]);
@@ -396,8 +396,8 @@ attn_bwd_dkv_kernel(AttnArgs a, const T* __restrict__ dctx, long long ld_d, cons
       float d = dp[j], pd = p;
       if (a.drop_thr) {
         const int q = q0 + lane, kk = kbase + warp * 4 + j;
-        const unsigned long long idx = (((unsigned long long)b * a.nh + h) * a.L + q) * (unsigned long long)Lk + kk;
-        const bool keep = dropout_keep(a.seed, idx, a.drop_thr);
+        const bool keep = attn_drop_keep(attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q), kk,
+                                         a.drop_thr);
         d = keep ? d * a.drop_scale : 0.f;
         pd = keep ? p * a.drop_scale : 0.f;
       }

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/mtvaf_b200.h"
 #include <cstdarg>
+#include <atomic>
 #include <cstring>
 
 namespace mtvaf {
@@ -14,6 +15,9 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};   // statistics only: kernels launched by this library
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int n = 0;   // read-only device-properties cache (the only global state of the library)
@@ -28,6 +32,7 @@ int sm_count() {
 }  // namespace mtvaf
 
 extern "C" int mtvaf_abi_version(void) { return MTVAF_ABI_VERSION; }
+extern "C" uint64_t mtvaf_launch_count(void) { return mtvaf::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* mtvaf_last_error(void) { return mtvaf::g_last_error; }
 extern "C" int mtvaf_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

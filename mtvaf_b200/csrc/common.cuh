@@ -25,7 +25,13 @@ void set_last_error(const char* fmt, ...);
       return -1;                                                                          \
     }                                                                                     \
   } while (0)
-#define MTVAF_LAUNCH_CHECK() MTVAF_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this check; it also counts launches (mtvaf_launch_count)
+void note_launch();
+#define MTVAF_LAUNCH_CHECK()              \
+  do {                                    \
+    ::mtvaf::note_launch();               \
+    MTVAF_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 
 int sm_count();
 
@@ -182,5 +188,41 @@ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
   return dropout_bits(seed, idx) >= threshold;
 }
+
+// ---- attention-probability dropout (modeling_roberta.py:268) -----------------------------------
+// The softmax kernels are issue-bound, so the mask costs ~4 integer ops per element: one 32-bit key per
+// (batch, head, query) row (attn_drop_rowkey, hashed once per row) and one 3-multiply hash per PAIR of keys
+// (reference key numbering: prefix rows 0..P-1, then text rows).  Forward, backward and the SIMT kernels all
+// derive the mask from these two functions, so backward regenerates forward's mask.
+__device__ __forceinline__ uint32_t attn_drop_rowkey(uint64_t seed, uint64_t row) { return dropout_bits(seed, row); }
+__device__ __forceinline__ void attn_drop_pair(uint32_t rowkey, uint32_t pair, uint32_t& h0, uint32_t& h1) {
+  uint32_t h = (pair ^ rowkey) * 0x9E3779B1u;
+  h ^= h >> 15;
+  h *= 0x85EBCA77u;
+  h0 = h;
+  h ^= h >> 16;
+  h1 = h * 0xC2B2AE3Du;
+}
+__device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int kk, uint32_t thr) {
+  uint32_t h0, h1;
+  attn_drop_pair(rowkey, static_cast<uint32_t>(kk) >> 1, h0, h1);
+  return ((kk & 1) ? h1 : h0) >= thr;
+}
+// keep flags of the 8 consecutive keys kk0 .. kk0+7 (kk0 >= 0)
+__device__ __forceinline__ void attn_drop_keep8(uint32_t rowkey, int kk0, uint32_t thr, bool (&keep)[8]) {
+  if ((kk0 & 1) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t h0, h1;
+      attn_drop_pair(rowkey, static_cast<uint32_t>(kk0 >> 1) + i, h0, h1);
+      keep[2 * i] = h0 >= thr;
+      keep[2 * i + 1] = h1 >= thr;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = attn_drop_keep(rowkey, kk0 + j, thr);
+  }
+}
+
 
 }  // namespace mtvaf

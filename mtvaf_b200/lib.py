@@ -76,6 +76,8 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     lib.mtvaf_last_error.restype = C.c_char_p
     lib.mtvaf_last_error.argtypes = []
+    lib.mtvaf_launch_count.restype = C.c_uint64
+    lib.mtvaf_launch_count.argtypes = []
     missing = []
     for name, argtypes in SIGNATURES.items():
         try:

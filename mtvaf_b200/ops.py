@@ -32,26 +32,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# kernels launched per C-ABI call (default 1): the bench reports the count of OUR launches
-_KERNELS_PER_CALL = {"embed_ln_fwd": 2, "attention_bwd": 3, "gate_bwd": 2, "mse": 1}
-_launches = 0
+# the library counts its own kernel launches (mtvaf_launch_count); the bench reports the count of OUR launches
+_launch_base = 0
 GEMM_EVENT_SINK = None      # bench.py: list receiving (start_event, end_event, flops) per tcgen05 GEMM launch
 
 
 def reset_launch_count():
-    global _launches
-    _launches = 0
+    global _launch_base
+    _launch_base = int(_raw.mtvaf_launch_count())
 
 
 def launch_count() -> int:
-    return _launches
+    return int(_raw.mtvaf_launch_count()) - _launch_base
 
 
 def _check(rc: int, name: str):
-    global _launches
     if rc != 0:
         raise L.MtvafError("%s failed (%d): %s" % (name, rc, L.last_error()))
-    _launches += _KERNELS_PER_CALL.get(name, 1)
 
 
 def _cuda(*ts):

@@ -344,8 +344,30 @@ def test_attention_dropout_consistency(ops):
     assert abs(float(fd) - float(dvp[1, 3, 5, 7])) < 1e-3 * (1 + abs(float(fd)))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_dropout_keep_rate(ops, dtype):
+    """With V == 1 every context element is sum_k keep_k p_k / (1-p): its mean over many rows is 1 and the
+    fraction of dropped probability mass is p (uniform probabilities: Q = K = 0)."""
+    B, Lq, P, nh, d, p = 8, 128, 16, 12, 64, 0.1
+    H = nh * d
+    qkv = torch.zeros(B * Lq, 3 * H, device=DEV, dtype=dtype)
+    qkv[:, 2 * H:] = 1.0
+    kp = torch.zeros(B, nh, P, d, device=DEV, dtype=dtype)
+    vp = torch.ones(B, nh, P, d, device=DEV, dtype=dtype)
+    mask = torch.ones(B, Lq, dtype=torch.long, device=DEV)
+    ctx, _, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p, seed=123)
+    kept = ctx.float().view(B * Lq, nh, d)[:, :, 0] * (1 - p)          # fraction of the 144 keys kept per row
+    assert abs(float(kept.mean()) - (1 - p)) < (5e-3 if dtype == torch.bfloat16 else 2e-3)   # bf16(1/144) is +0.2%
+    # per-row keep counts are binomial(144, 0.9): variance of the fraction = p(1-p)/144
+    var = float(kept.var())
+    assert 0.5 * p * (1 - p) / (P + Lq) < var < 1.6 * p * (1 - p) / (P + Lq)
+    ctx2, _, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p, seed=124)
+    assert not torch.equal(ctx, ctx2)
+
+
 @pytest.mark.parametrize("B,Lq,P,p_drop", [(2, 128, 16, 0.1), (3, 40, 36, 0.1), (2, 100, 5, 0.0), (4, 128, 64, 0.1),
-                                            (2, 128, 0, 0.1), (1, 17, 4, 0.0)])
+                                            (2, 128, 0, 0.1), (1, 17, 4, 0.0), (2, 64, 5, 0.1), (32, 128, 16, 0.1),
+                                            (13, 96, 36, 0.0)])
 def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
     """The tcgen05 forward/backward kernels and the SIMT kernels share one dropout hash: on bf16 inputs they
     must agree to bf16 rounding, with and without probability dropout, including ragged key masks."""
