@@ -84,6 +84,11 @@ int mtvaf_set_gemm_impl(int impl);
 int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, const MtvafEpilogue* epi, int splits, void* stream);
 
+/* out[m, n] = sum_k x[m, k] w[n, k] + bias[n] for skinny outputs N <= 48 (tag head fc 768->11, bert_model.py:510;
+ * the 12 gate projectors as one [48, 6144] matrix, :566-569): warp-per-row, no split-K, bitwise reproducible. */
+int mtvaf_skinny_linear_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int M, int N,
+                            int K, float* out, int64_t ldo, void* stream);
+
 /* ---- elementwise / reductions --------------------------------------------------------------- */
 int mtvaf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int mtvaf_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
@@ -162,11 +167,19 @@ int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void* qkv, int6
  * (slot 1): kv_out[l,s,b,(j*4+r)*hid + c] = sum_i gate[l,(j,b),i] * guids[j,b,r,i*2*hid + s*hid + c]. */
 int mtvaf_gate_fwd(const void* guids, const float* gate_logits, int n_layers, int n_img, int B, int hid,
                    void* kv_out, float* gates_out, int dtype, void* stream);
-/* d_kv: [n_layers, 2, B, P*hid] fp32.  d_guids (fp32 [n_img,B,4,8*hid]) is ACCUMULATED (+=);
- * d_gates_scratch [n_img*B, n_layers*4] fp32 must be zeroed by the caller; d_gate_logits same shape (written). */
+/* d_kv: [n_layers, 2, B, P*hid] fp32.  d_guids (fp32 [n_img,B,4,8*hid]) is WRITTEN (the gate path's share of the
+ * prompt gradient); d_gates_scratch [n_img*B, n_layers*4] fp32 must be zeroed by the caller; d_gate_logits same
+ * shape (written). */
 int mtvaf_gate_bwd(const float* d_kv, const void* guids, const float* gate_logits, const float* gates, int n_layers,
                    int n_img, int B, int hid, float* d_guids, float* d_gates_scratch, float* d_gate_logits,
                    int dtype, void* stream);
+/* out[row, r, w] = d_guids[row, r, w] + ( d_gs[row, r*S + w % S] + dropout(d_gm[row, w]) ) / 4 with S = W/4:
+ * the gate path plus the backward of both 4-way means of get_visual_prompt (bert_model.py:550,567), written once
+ * in the dtype of the GEMMs that consume it.  d_gs (fp32 [rows, W], gradient of the mode-1 mean) and d_gm
+ * ([rows, W] of gm_dtype, gradient of the ANP-head input after img_dropout, bert_model.py:551; the dropout mask
+ * (p_drop, seed, element index row*W + w) is re-applied here) may each be NULL. */
+int mtvaf_prompt_grad_combine(const float* d_guids, const float* d_gs, const void* d_gm, int gm_dtype, float p_drop,
+                              uint64_t seed, int64_t rows, int W, void* out, int out_dtype, void* stream);
 /* 4-way means of the prompt x [rows, 4, W] -> y [rows, W]:
  *   mode 0: y[row, w]       = mean_r x[row, r, w]                      (guids.mean(dim=1), bert_model.py:550)
  *   mode 1: y[row, r*S + c] = mean_i x[row, r, i*S + c], S = W/4       (stack(split).sum(0)/4, bert_model.py:567)

@@ -115,6 +115,47 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Skinny linear layer out[m, n] = sum_k x[m, k] w[n, k] + b[n] for N <= 48 (the tag head fc 768->11,
+// bert_model.py:510, and the 12 gate projectors 6144->4 applied as one [48, 6144] matrix, :566-569).
+// HBM/L2-bound: one warp per row, lanes split K in float4 pieces (coalesced 512 B per warp and step), the N
+// accumulators live in registers and are reduced with shuffles at the end.  No split-K, no atomics:
+// the result is bitwise reproducible, which the 128x128-tile kernel above cannot offer for these shapes
+// without wasting > 90 % of its FMAs (N = 11) or serialising K on 8 blocks (M = 1024, K = 6144).
+template <int NT>
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w, long long ldw,
+                     const float* __restrict__ bias, int M, int N, int K, float* __restrict__ out, long long ldo) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    const float* xr = x + (long long)m * ldx;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + k);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (n < N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(w + (long long)n * ldw + k));
+          acc[n] = fmaf(a.x, b.x, acc[n]);
+          acc[n] = fmaf(a.y, b.y, acc[n]);
+          acc[n] = fmaf(a.z, b.z, acc[n]);
+          acc[n] = fmaf(a.w, b.w, acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (n < N) {
+        const float s = warp_sum(acc[n]);
+        if (lane == 0) out[(long long)m * ldo + n] = s + (bias ? bias[n] : 0.f);
+      }
+    }
+  }
+}
+
 }  // namespace mtvaf
 
 using namespace mtvaf;
@@ -144,6 +185,23 @@ extern "C" int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const 
     gemm_f32_kernel<true, true><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
   else
     gemm_f32_kernel<true, false><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_skinny_linear_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                                       int M, int N, int K, float* out, int64_t ldo, void* stream) {
+  MTVAF_REQUIRE(x && w && out && M > 0 && N > 0 && K > 0, "skinny_linear: bad argument");
+  MTVAF_REQUIRE(N <= 48, "skinny_linear: N=%d > 48 (use mtvaf_gemm_f32)", N);
+  MTVAF_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(w) % 16 == 0,
+                "skinny_linear: K / leading dims must be multiples of 4 and x, w 16-byte aligned");
+  long long blocks = ((long long)M + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N <= 16) skinny_linear_kernel<16><<<(int)blocks, 256, 0, st>>>(x, ldx, w, ldw, bias, M, N, K, out, ldo);
+  else skinny_linear_kernel<48><<<(int)blocks, 256, 0, st>>>(x, ldx, w, ldw, bias, M, N, K, out, ldo);
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -58,34 +58,107 @@ gate_fwd_kernel(const T* __restrict__ guids, const float* __restrict__ logits, i
   }
 }
 
+// backward of the gate-weighted sums: one block per (row = j*B + b, r) as in forward.  Each thread keeps its
+// columns' four split values and their gradient accumulators in registers across ALL layers, so the prompt
+// (guids) is read once, d_guids is written once (plain store) and d_kv is streamed exactly once; the per-layer
+// gate gradients are reduced warp-wise into shared memory and leave the block as one atomic per (layer, split).
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_bwd_kernel(const float* __restrict__ d_kv, const T* __restrict__ guids, const float* __restrict__ gates,
                 int n_layers, int n_img, int B, int hid, float* __restrict__ d_guids, float* __restrict__ d_gates) {
-  __shared__ float red[32];
+  extern __shared__ float part[];                     // [8 warps][n_layers * 4]
+  constexpr int KMAX = 8;                             // columns per thread: 2*hid <= 2048
   const int rowr = blockIdx.x;
   const int row = rowr >> 2, r = rowr & 3;
   const int j = row / B, b = row - j * B;
   const int S2 = 2 * hid, W = 4 * S2, P = 4 * n_img;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* src = guids + ((long long)row * 4 + r) * W;
   float* dsrc = d_guids + ((long long)row * 4 + r) * W;
   const long long kv_stride_l = 2LL * B * P * hid;
+  float x[KMAX][4], acc[KMAX][4];
+  long long off[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int c = threadIdx.x + k * 256;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[k][i] = c < S2 ? to_f<T>(src[i * S2 + c]) : 0.f; acc[k][i] = 0.f; }
+    const int slot = c / hid, cc = c - slot * hid;
+    off[k] = ((long long)slot * B + b) * P * hid + (long long)(j * 4 + r) * hid + cc;
+  }
+  const float* grow = gates + (long long)row * n_layers * 4;
   for (int l = 0; l < n_layers; ++l) {
-    const float g0 = gates[(long long)row * n_layers * 4 + l * 4 + 0], g1 = gates[(long long)row * n_layers * 4 + l * 4 + 1],
-                g2 = gates[(long long)row * n_layers * 4 + l * 4 + 2], g3 = gates[(long long)row * n_layers * 4 + l * 4 + 3];
+    const float g0 = grow[l * 4 + 0], g1 = grow[l * 4 + 1], g2 = grow[l * 4 + 2], g3 = grow[l * 4 + 3];
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-    for (int c = threadIdx.x; c < S2; c += blockDim.x) {
-      const int slot = c / hid, cc = c - slot * hid;
-      const float d = d_kv[l * kv_stride_l + ((long long)slot * B + b) * P * hid + (long long)(j * 4 + r) * hid + cc];
-      p0 += d * to_f<T>(src[c]); p1 += d * to_f<T>(src[S2 + c]);
-      p2 += d * to_f<T>(src[2 * S2 + c]); p3 += d * to_f<T>(src[3 * S2 + c]);
-      dsrc[c] += g0 * d; dsrc[S2 + c] += g1 * d; dsrc[2 * S2 + c] += g2 * d; dsrc[3 * S2 + c] += g3 * d;
+    const float* dl = d_kv + l * kv_stride_l;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int c = threadIdx.x + k * 256;
+      if (c < S2) {
+        const float d = dl[off[k]];
+        p0 += d * x[k][0]; p1 += d * x[k][1]; p2 += d * x[k][2]; p3 += d * x[k][3];
+        acc[k][0] += g0 * d; acc[k][1] += g1 * d; acc[k][2] += g2 * d; acc[k][3] += g3 * d;
+      }
     }
-    p0 = block_sum(p0, red); p1 = block_sum(p1, red); p2 = block_sum(p2, red); p3 = block_sum(p3, red);
-    if (threadIdx.x == 0) {
-      float* dg = d_gates + (long long)row * n_layers * 4 + l * 4;
-      atomicAdd(dg + 0, p0); atomicAdd(dg + 1, p1); atomicAdd(dg + 2, p2); atomicAdd(dg + 3, p3);
+    p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2); p3 = warp_sum(p3);
+    if (lane == 0) {
+      float* pp = part + warp * n_layers * 4 + l * 4;
+      pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
     }
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int c = threadIdx.x + k * 256;
+    if (c < S2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dsrc[i * S2 + c] = acc[k][i];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_layers * 4; idx += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w * n_layers * 4 + idx];
+    atomicAdd(d_gates + (long long)row * n_layers * 4 + idx, s);
+  }
+}
+
+// d(prompt) assembled in one pass, in the dtype of the GEMMs that consume it:
+//   out[row, r, w] = d_guids[row, r, w] + ( d_gs[row, r*S + w % S] + dropout(d_gm[row, w]) ) / 4,   S = W / 4
+// i.e. the gate path plus the backward of the two 4-way means of get_visual_prompt (bert_model.py:550,567);
+// d_gm is the gradient of the ANP-head input BEFORE img_dropout (the mask is regenerated here).
+template <typename TO, typename TM>
+__global__ void __launch_bounds__(256)
+prompt_grad_combine_kernel(const float* __restrict__ d_guids, const float* __restrict__ d_gs,
+                           const TM* __restrict__ d_gm, long long rows, int W, TO* __restrict__ out,
+                           uint32_t drop_thr, float drop_scale, unsigned long long seed) {
+  const int S = W / 4;
+  const long long n8 = rows * 4 * (W / 8);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const long long e = i * 8;
+    const long long row = e / (4LL * W);
+    const int rem = (int)(e - row * 4LL * W);
+    const int r = rem / W, w = rem - r * W;
+    float v[8];
+    Vec8<float>::load(d_guids + e, v);
+    if (d_gs) {
+      float g[8];
+      Vec8<float>::load(d_gs + row * W + r * S + (w % S), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += 0.25f * g[k];
+    }
+    if (d_gm) {
+      float g[8];
+      Vec8<TM>::load(d_gm + row * W + w, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float x = g[k];
+        if (drop_thr) x = dropout_keep(seed, (unsigned long long)(row * W + w + k), drop_thr) ? x * drop_scale : 0.f;
+        v[k] += 0.25f * x;
+      }
+    }
+    Vec8<TO>::store(out + e, v);
   }
 }
 
@@ -217,9 +290,10 @@ crf_nll_kernel(const float* __restrict__ em, const long long* __restrict__ tags,
                float* __restrict__ d_end, float* __restrict__ d_trans, float gs) {
   extern __shared__ float alpha[];                 // [L][T]
   __shared__ float tr[CRF_MAX_T * CRF_MAX_T];
+  __shared__ float dtr[CRF_MAX_T * CRF_MAX_T];     // this sequence's transition gradient (lane t owns row t)
   const int b = blockIdx.x, t = threadIdx.x;
   const bool act = t < T;
-  for (int i = t; i < T * T; i += 32) tr[i] = trans[i];
+  for (int i = t; i < T * T; i += 32) { tr[i] = trans[i]; dtr[i] = 0.f; }
   int len = 0;
   for (int i = t; i < L; i += 32) len += (mask[(long long)b * L + i] != 0);
   len = (int)(warp_sum((float)len) + 0.5f);
@@ -287,13 +361,17 @@ crf_nll_kernel(const float* __restrict__ em, const long long* __restrict__ tags,
       nb_mx = fmaxf(nb_mx, v);
       if (act && d_trans) {
         const float pm = __expf(ap + v - logz);
-        atomicAdd(d_trans + t * T + u, (pm - ((t == gprev && u == gold) ? 1.f : 0.f)) * gs);
+        dtr[t * T + u] += (pm - ((t == gprev && u == gold) ? 1.f : 0.f)) * gs;   // one atomic per entry at the end
       }
     }
     float se = 0.f;
 #pragma unroll 1
     for (int u = 0; u < T; ++u) se += act ? __expf(vals[u] - nb_mx) : 0.f;
     beta = act ? nb_mx + __logf(se) : -INFINITY;
+  }
+  if (d_trans) {
+    __syncwarp();
+    for (int i = t; i < T * T; i += 32) atomicAdd(d_trans + i, dtr[i]);
   }
 }
 
@@ -371,18 +449,50 @@ extern "C" int mtvaf_gate_bwd(const float* d_kv, const void* guids, const float*
                               float* d_gate_logits, int dtype, void* stream) {
   MTVAF_REQUIRE(d_kv && guids && gate_logits && gates && d_guids && d_gates_scratch && d_gate_logits,
                 "gate_bwd: null argument");
+  MTVAF_REQUIRE(n_layers > 0 && n_img > 0 && B > 0 && hid > 0 && 2 * hid <= 2048, "gate_bwd: bad shape (hid <= 1024)");
   const int blocks = n_img * B * 4;
+  const size_t sm = (size_t)8 * n_layers * 4 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MTVAF_BF16)
-    gate_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(d_kv, (const __nv_bfloat16*)guids, gates, n_layers, n_img,
-                                                           B, hid, d_guids, d_gates_scratch);
+    gate_bwd_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>(d_kv, (const __nv_bfloat16*)guids, gates, n_layers, n_img,
+                                                            B, hid, d_guids, d_gates_scratch);
   else
-    gate_bwd_kernel<float><<<blocks, 256, 0, st>>>(d_kv, (const float*)guids, gates, n_layers, n_img, B, hid, d_guids,
-                                                   d_gates_scratch);
+    gate_bwd_kernel<float><<<blocks, 256, sm, st>>>(d_kv, (const float*)guids, gates, n_layers, n_img, B, hid, d_guids,
+                                                    d_gates_scratch);
   MTVAF_LAUNCH_CHECK();
   const long long groups = (long long)n_img * B * n_layers;
   gate_logit_bwd_kernel<<<(int)((groups + 255) / 256), 256, 0, st>>>(d_gates_scratch, gates, gate_logits, groups,
                                                                      d_gate_logits);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_prompt_grad_combine(const float* d_guids, const float* d_gs, const void* d_gm, int gm_dtype,
+                                         float p_drop, uint64_t seed, int64_t rows, int W, void* out, int out_dtype,
+                                         void* stream) {
+  MTVAF_REQUIRE(d_guids && out && rows > 0 && W > 0 && W % 32 == 0, "prompt_grad_combine: bad argument (W %% 32 == 0)");
+  MTVAF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "prompt_grad_combine: bad dropout p");
+  uint32_t thr = 0;
+  float scale = 1.f;
+  if (p_drop > 0.f && d_gm) {
+    const double t = (double)p_drop * 4294967296.0;
+    thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    scale = 1.f / (1.f - p_drop);
+  }
+  const long long n8 = rows * 4 * (W / 8);
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MTVAF_PGC(TO_, TM_)                                                                                       \
+  prompt_grad_combine_kernel<TO_, TM_><<<(int)blocks, 256, 0, st>>>(d_guids, d_gs, (const TM_*)d_gm, rows, W,    \
+                                                                    (TO_*)out, thr, scale, seed)
+  const bool ob = out_dtype == MTVAF_BF16, mb = gm_dtype == MTVAF_BF16;
+  if (ob && mb) MTVAF_PGC(__nv_bfloat16, __nv_bfloat16);
+  else if (ob) MTVAF_PGC(__nv_bfloat16, float);
+  else if (mb) MTVAF_PGC(float, __nv_bfloat16);
+  else MTVAF_PGC(float, float);
+#undef MTVAF_PGC
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

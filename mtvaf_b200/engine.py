@@ -420,10 +420,7 @@ class Engine:
         # all 12 projectors in one skinny GEMM: [rows, 8H] x [n_layers*4, 8H]^T
         pw, pb = self._projector_pack()
         gs32 = ops.cast_f32(gs) if gs.dtype == BF16 else gs
-        # skinny fp32 GEMM (N = 48): split K over the grid, partial sums accumulate onto the broadcast bias
-        gate_logits = pb.unsqueeze(0).repeat(rows, 1)
-        ops.gemm(gs32, pw, M=rows, N=4 * c.n_layers, K=W8, mode=L.EPI_ATOMIC_F32, out=gate_logits,
-                 splits=ops.skinny_splits(rows, 4 * c.n_layers, W8))
+        gate_logits = ops.skinny_linear(gs32, pw, pb)            # [rows, 48], deterministic (no split-K atomics)
         kv, gates = ops.gate_fwd(guids, gate_logits, c.n_layers, n_img, B, H)
         saved.update(gs32=gs32, gate_logits=gate_logits, gates=gates)
         return kv, img_losses, (saved if save else None)
@@ -442,8 +439,9 @@ class Engine:
         n_img, B, H = saved["n_img"], saved["B"], c.H
         W8 = 8 * H
         rows, rows4 = n_img * B, n_img * B * 4
+        cd = self.compute_dtype
         guids = saved["guids"]
-        d_guids = torch.zeros((rows4, W8), dtype=F32, device=guids.device)
+        d_guids = torch.empty((rows4, W8), dtype=F32, device=guids.device)      # written by gate_bwd
         d_gate_logits = ops.gate_bwd(dkv, guids, saved["gate_logits"], saved["gates"], c.n_layers, n_img, B, H,
                                      d_guids)
         # projector GEMM backward (fp32 skinny)
@@ -456,14 +454,13 @@ class Engine:
             ops.add_inplace(f.g("projectors.%d.weight" % l), dpw[4 * l:4 * l + 4].contiguous())
             ops.add_inplace(f.g("projectors.%d.bias" % l), dpb[4 * l:4 * l + 4].contiguous())
         d_gs = ops.linear_dgrad(d_gate_logits, pw)                                               # [rows, 8H] fp32
-        ops.mean4_bwd_add(d_gs, d_guids, rows, W8, 1)
+        d_gmd, p_i, seed_i = None, 0.0, 0
         if saved["vao"] and saved["dlogits"] is not None and d_img_losses is not None:
             dlog = saved["dlogits"]
             n_anp = saved["n_anp"]
             # scale each head's rows by the weight of its loss (device scalars, no sync)
             for j in range(n_img):
                 ops.scale_by_device_scalar(dlog[j * B:(j + 1) * B], d_img_losses[j:j + 1])
-            cd = self.compute_dtype
             dl = ops.cast_bf16(dlog) if cd == BF16 else dlog
             d_gmd = torch.empty((rows, W8), dtype=cd, device=guids.device)
             for j, nm in enumerate(saved["names"]):
@@ -471,12 +468,9 @@ class Engine:
                 ops.linear_wgrad(dj, saved["gmd"][j * B:(j + 1) * B], f.g(nm + ".weight"), n_valid=n_anp)
                 ops.colsum(dj, f.g(nm + ".bias"), n_valid=n_anp)
                 ops.gemm(dj, self.cw(nm + ".weight"), b_mn=True, M=B, N=W8, K=n_anp, out=d_gmd[j * B:(j + 1) * B])
-            if saved["p_i"] > 0:
-                d_gmd = ops.dropout_apply(d_gmd, saved["p_i"], saved["seed_i"])
-            d_gm = ops.cast_f32(d_gmd) if d_gmd.dtype == BF16 else d_gmd
-            ops.mean4_bwd_add(d_gm, d_guids, rows, W8, 0)
-        cd = self.compute_dtype
-        dg = ops.cast_bf16(d_guids) if cd == BF16 else d_guids
+            p_i, seed_i = saved["p_i"], saved["seed_i"]
+        # gate path + both 4-way-mean backward terms (+ img_dropout mask) in one pass, in the GEMM dtype
+        dg = ops.prompt_grad_combine(d_guids, d_gs, d_gmd, p_i, seed_i, rows, W8, cd)
         ops.linear_wgrad(dg, saved["h1"], f.g("encoder_conv.2.weight"))
         ops.colsum(dg, f.g("encoder_conv.2.bias"))
         dh1 = ops.linear_dgrad(dg, self.cw("encoder_conv.2.weight"), mode=L.EPI_MUL_DTANH, aux=saved["h1"])
@@ -495,7 +489,10 @@ class Engine:
         p_d = 0.1 if training else 0.0                                             # self.dropout, bert_model.py:466,506
         seq_d = ops.dropout_apply(seq32, p_d, self.seed(910)) if p_d > 0 else seq32
         n_tags = f.params["fc.weight"].shape[0]
-        em = ops.linear_fwd(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
+        if n_tags <= 48 and H % 4 == 0:
+            em = ops.skinny_linear(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
+        else:
+            em = ops.linear_fwd(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
         crf = (f.w("crf.start_transitions"), f.w("crf.end_transitions"), f.w("crf.transitions"))
         best, lens = ops.crf_decode(em, mask, *crf)
         out = dict(emissions=em, best=best, lens=lens, loss=None, prob_loss=None)

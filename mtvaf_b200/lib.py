@@ -36,6 +36,7 @@ SIGNATURES = {
     "mtvaf_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
     "mtvaf_set_gemm_impl": [_i],
     "mtvaf_gemm_f32": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
+    "mtvaf_skinny_linear_f32": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp],
     "mtvaf_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mtvaf_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "mtvaf_colsum": [_vp, _i64, _i, _i, _i, _vp, _vp],
@@ -55,6 +56,7 @@ SIGNATURES = {
                             _vp, _vp, _i, _f, _u64, _vp],
     "mtvaf_gate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "mtvaf_gate_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "mtvaf_prompt_grad_combine": [_vp, _vp, _vp, _i, _f, _u64, _i64, _i, _vp, _i, _vp],
     "mtvaf_mean4_fwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "mtvaf_mean4_bwd_add": [_vp, _vp, _i64, _i, _i, _vp],
     "mtvaf_softmax_kl_fwd_bwd": [_vp, _i64, _vp, _i, _i, _i, _vp, _vp, _f, _vp],

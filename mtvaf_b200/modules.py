@@ -151,6 +151,7 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine: Engine, ids, tts, mask, training, want_probs, embeds, anchor, kv):
         need_grad = any(ctx.needs_input_grad)       # grad mode is off inside Function.forward
+        ctx.set_materialize_grads(False)            # unused hidden states arrive as None, not as zero tensors
         hs, saved, attns = engine.encoder_fwd(ids, tts, mask, kv, training, need_grad, want_probs, embeds)
         ctx.engine, ctx.saved = engine, saved
         ctx.kv_grad = kv is not None and kv.requires_grad

@@ -141,6 +141,18 @@ def wgrad_splits(m_out: int, n_out: int, k: int, bf16: bool) -> int:
     return best
 
 
+def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 y = x w^T + b for N = w.shape[0] <= 48: deterministic warp-per-row kernel (no split-K atomics)."""
+    _cuda(x, w, bias)
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    _check(_raw.mtvaf_skinny_linear_f32(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), M, N, K,
+                                        out.data_ptr(), out.stride(0), _stream()), "skinny_linear")
+    return out
+
+
 def skinny_splits(M: int, N: int, K: int) -> int:
     """split-K factor for the fp32 SIMT GEMM when the output has too few 128x128 tiles to fill the SMs."""
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
@@ -323,6 +335,15 @@ def gate_bwd(d_kv, guids, gate_logits, gates, n_layers, n_img, B, hid, d_guids):
                                n_img, B, hid, d_guids.data_ptr(), scratch.data_ptr(), d_logits.data_ptr(), dt(guids),
                                _stream()), "gate_bwd")
     return d_logits
+
+
+def prompt_grad_combine(d_guids, d_gs, d_gm, p_drop, seed, rows, W, out_dtype):
+    """d(prompt) = gate path + both 4-way-mean backward terms, one pass, written in `out_dtype`."""
+    out = torch.empty((rows * 4, W), dtype=out_dtype, device=d_guids.device)
+    _check(_raw.mtvaf_prompt_grad_combine(d_guids.data_ptr(), _p(d_gs), _p(d_gm), dt(d_gm) if d_gm is not None else F32,
+                                          p_drop, seed, rows, W, out.data_ptr(), dt(out), _stream()),
+           "prompt_grad_combine")
+    return out
 
 
 def softmax_kl(logits, n, target, B, want_grad, grad_scale=1.0):

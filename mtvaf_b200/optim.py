@@ -119,6 +119,11 @@ class GradSync:
             engine.layer_grad_hook = self._on_layer
 
     def _reduce(self, t: torch.Tensor):
+        if not t.is_cuda:
+            # host tensors (gloo; the CPU tests of this bookkeeping): synchronous SUM then 1/world
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+            return
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.side):

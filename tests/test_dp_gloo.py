@@ -1,0 +1,99 @@
+"""Host-side logic of the data-parallel path on CPU: world_size-2 `gloo` process group.
+
+GradSync replaces the reference's broken modules/parallel.py: every slice of the flat gradient buffer must be
+all-reduced (averaged) exactly once per step, whether its layer hook fired during backward or not."""
+import os
+import socket
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_engine(total, layer_ranges, rank):
+    g = torch.Generator().manual_seed(100 + rank)
+    G = torch.randn(total, generator=g)
+    flat = SimpleNamespace(G=G, layer_ranges=layer_ranges, total=total)
+    return SimpleNamespace(flat=flat, layer_grad_hook=None, tail_grad_hook=None)
+
+
+def _worker(rank, world, port, fired, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mtvaf_b200.optim import GradSync
+        layer_ranges = [(64, 200), (256, 400), (448, 640)]       # gaps = alignment padding
+        total = 1024
+        eng = _fake_engine(total, layer_ranges, rank)
+        expect = sum(_fake_engine(total, layer_ranges, r).flat.G for r in range(world)) / world
+        sync = GradSync(eng)
+        assert eng.layer_grad_hook is not None                   # hook installed for world > 1
+        for step in range(2):                                    # state must reset between steps
+            if step == 1:
+                eng.flat.G.copy_(_fake_engine(total, layer_ranges, rank).flat.G)
+            for i in fired:                                      # backward order: last layer first
+                eng.layer_grad_hook(i)
+            sync.finish()
+            covered = torch.zeros(total, dtype=torch.bool)
+            covered[:64] = True
+            for a, b in layer_ranges:
+                covered[a:b] = True
+            covered[640:] = True
+            assert torch.allclose(eng.flat.G[covered], expect[covered], atol=1e-6), "step %d" % step
+            assert not sync.works and not sync.done_layers
+        q.put((rank, "ok"))
+    except Exception as e:                                       # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fired", [(2, 1, 0), (2,), ()])
+def test_gradsync_world2_gloo(fired):
+    from mtvaf_b200 import build
+    build.build()                                                # the workers import the package (loads the .so)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fired, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_adamw_ranges_follow_reference_groups():
+    """modules/train.py:894-926: 'bert' and 'encoder_conv' at args.lr, 'crf'/'fc' at 5e-2, everything else
+    (projectors, ANP heads, probe) never updated."""
+    from mtvaf_b200 import build
+    build.build()
+    from mtvaf_b200.optim import reference_groups
+    groups = reference_groups(5e-5)
+
+    def hit(name):
+        for pred, lr, wd in groups:
+            if pred(name):
+                return lr, wd
+        return None
+
+    assert hit("bert.encoder.layer.3.output.dense.weight") == (5e-5, 1e-2)
+    assert hit("encoder_conv.0.weight") == (5e-5, 1e-2)
+    assert hit("crf.transitions") == (5e-2, 1e-2)
+    assert hit("fc.weight") == (5e-2, 1e-2)
+    assert hit("projectors.3.weight") is None
+    assert hit("img_classifier.weight") is None
+    assert hit("oneWordpsdProbe.oneWordpsdProbe.proj") is None

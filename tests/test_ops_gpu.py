@@ -430,7 +430,7 @@ def test_gate_and_mean4(ops, dtype):
     assert rel_err(kv, ref) < tol
     dkv = rnd(*ref.shape, seed=3)
     ref.backward(dkv)
-    d_guids = torch.zeros(n_img, B, 4, W, device=DEV)
+    d_guids = torch.full((n_img, B, 4, W), 7.0, device=DEV)       # gate_bwd WRITES (no pre-zeroing needed)
     d_logits = ops.gate_bwd(dkv, guids, logits.detach(), gates, n_layers, n_img, B, hid, d_guids)
     assert rel_err(d_guids, gf.grad) < tol
     assert rel_err(d_logits, logits.grad) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
@@ -444,6 +444,38 @@ def test_gate_and_mean4(ops, dtype):
     x = torch.zeros(n_img * B, 4, W, device=DEV, requires_grad=True)
     (torch.stack(x.split(2 * hid, -1)).sum(0).view(n_img * B, -1) / 4 * dy).sum().backward()
     assert rel_err(dx, x.grad) < 1e-6
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_prompt_grad_combine(ops, out_dtype):
+    """One-pass assembly of d(prompt): gate path + backward of both 4-way means (+ img_dropout mask)."""
+    rows, hid = 6, 768
+    W = 8 * hid
+    d_guids = rnd(rows * 4, W, seed=1)
+    d_gs = rnd(rows, W, seed=2)
+    d_gm = rnd(rows, W, seed=3, dtype=out_dtype)
+    ref = d_guids.clone().view(rows, 4, W)
+    dx = torch.zeros(rows, 4, W, device=DEV)
+    ops.mean4_bwd_add(d_gs, dx, rows, W, 1)
+    p = 0.2
+    gm_d = ops.dropout_apply(d_gm, p, 901)
+    ops.mean4_bwd_add(gm_d.float(), dx, rows, W, 0)
+    ref = ref + dx
+    out = ops.prompt_grad_combine(d_guids, d_gs, d_gm, p, 901, rows, W, out_dtype)
+    assert out.dtype == out_dtype
+    assert rel_err(out, ref.view(rows * 4, W)) < (1e-2 if out_dtype == torch.bfloat16 else 1e-6)
+    out2 = ops.prompt_grad_combine(d_guids, None, None, 0.0, 0, rows, W, torch.float32)
+    assert torch.equal(out2, d_guids)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 48, 6144), (4099, 11, 768), (7, 3, 64), (300, 16, 1024)])
+def test_skinny_linear(ops, M, N, K):
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    y = ops.skinny_linear(x, w, b)
+    ref = x.double() @ w.double().t() + b.double()
+    assert rel_err(y, ref) < 1e-5
+    assert torch.equal(y, ops.skinny_linear(x, w, b))          # bitwise reproducible
+    assert rel_err(ops.skinny_linear(x, w), x.double() @ w.double().t()) < 1e-5
 
 
 def test_softmax_kl(ops):
