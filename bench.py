@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--per-gpu-batch", type=int, default=int(os.environ.get("MTVAF_BENCH_BATCH", 256)))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="issue every launch from Python each step instead of replaying the whole-step CUDA graph")
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     return ap.parse_args()
 
@@ -208,9 +210,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
-    for i in range(args.warmup):
-        step(resident[i % n_host])
+    # ---- warm-up (eager), then capture the whole step into one CUDA graph and warm the replay path
+    graphed = None
+    if args.no_graph:
+        for i in range(args.warmup):
+            step(resident[i % n_host])
+        run = step
+    else:
+        from mtvaf_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, resident[0], grad_sync=sync, warmup=args.warmup)
+        for i in range(args.warmup):
+            graphed(resident[i % n_host])
+        run = graphed
     barrier()
 
     # ---- timed region 1: inputs resident in HBM -> `value`
@@ -218,16 +229,14 @@ def main():
     if rank == 0:
         sampler.start()
     ops.reset_launch_count()
-    ops.GEMM_EVENT_SINK = gemm_events
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(args.steps):
-        loss = step(resident[i % n_host])
+        loss = run(resident[i % n_host])
     e1.record()
     barrier()
-    ops.GEMM_EVENT_SINK = None
-    launches = ops.launch_count()
+    launches = ops.launch_count() if graphed is None else graphed.kernels_per_replay * args.steps
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
@@ -238,8 +247,20 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
     final_loss = float(loss.detach())
 
-    # dominant kernel: the tcgen05 GEMM.  achieved = algorithmic 2*M*N*K summed over the launches of the
-    # timed region / summed CUDA-event durations of those launches (events recorded on the launch stream)
+    # ---- dominant kernel: the tcgen05 GEMM, timed per launch with CUDA events on the launch stream in a short
+    # EAGER pass (events cannot be read inside a graph replay).  achieved = algorithmic 2*M*N*K summed over the
+    # launches / summed event durations of those launches
+    n_prof = max(1, min(args.steps, 3))
+    ops.GEMM_EVENT_SINK = gemm_events
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    for i in range(n_prof):
+        step(resident[i % n_host])
+    p1.record()
+    barrier()
+    ops.GEMM_EVENT_SINK = None
+    eager_ms = p0.elapsed_time(p1) / n_prof
     g_fl = sum(f for (_, _, f) in gemm_events)
     g_ms = sum(a.elapsed_time(b) for (a, b, _) in gemm_events)
     peaks = {}
@@ -249,33 +270,47 @@ def main():
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    gemm_ms_per_step = g_ms / n_prof
 
     # ---- timed region 2: end to end through the public API with HOST buffers (pinned) -> `e2e`
-    copy_stream = torch.cuda.Stream()
-
-    def h2d(hb):
-        with torch.cuda.stream(copy_stream):
-            d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return d, ev
-
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    nxt = h2d(host[0])
-    for i in range(args.steps):
-        cur, ev = nxt
-        torch.cuda.current_stream().wait_event(ev)
-        for v in cur.values():                            # allocated on the copy stream, consumed on this one
-            v.record_stream(torch.cuda.current_stream())
-        if i + 1 < args.steps:
-            nxt = h2d(host[(i + 1) % n_host])            # prefetch the next batch behind this step's compute
-        l = step(cur)
-        loss_host.copy_(l.detach().reshape(()), non_blocking=True)   # D2H read of the step's result
-    e3.record()
-    barrier()
+    if graphed is not None:
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        graphed.prefetch(host[0])
+        for i in range(args.steps):
+            l = graphed(None)                                 # consume the staged batch, replay the step
+            if i + 1 < args.steps:
+                graphed.prefetch(host[(i + 1) % n_host])      # H2D of the next batch behind this replay
+            loss_host.copy_(l.reshape(()), non_blocking=True)         # D2H read of the step's result
+        e3.record()
+        barrier()
+    else:
+        copy_stream = torch.cuda.Stream()
+
+        def h2d(hb):
+            with torch.cuda.stream(copy_stream):
+                d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d, ev
+
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        nxt = h2d(host[0])
+        for i in range(args.steps):
+            cur, ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            for v in cur.values():                            # allocated on the copy stream, consumed on this one
+                v.record_stream(torch.cuda.current_stream())
+            if i + 1 < args.steps:
+                nxt = h2d(host[(i + 1) % n_host])            # prefetch the next batch behind this step's compute
+            l = step(cur)
+            loss_host.copy_(l.detach().reshape(()), non_blocking=True)   # D2H read of the step's result
+        e3.record()
+        barrier()
     t = torch.tensor([e2.elapsed_time(e3)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -292,6 +327,8 @@ def main():
                        "per_gpu_batch": B, "global_batch": B * world, "seq_len": L_TEXT, "prefix_rows": 16,
                        "parallelism": "dp%d" % world,
                        "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "launch": "eager (one Python/ctypes call per kernel)" if graphed is None else
+                                 "whole step (fwd+bwd+all-reduce+AdamW) replayed from one CUDA graph",
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4},
@@ -300,7 +337,10 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback",
-                         "gemm_launches": len(gemm_events), "gemm_share_of_step": g_ms / ms if ms else None,
+                         "gemm_launches_per_step": len(gemm_events) // n_prof,
+                         "gemm_ms_per_step": gemm_ms_per_step,
+                         "gemm_share_of_step": gemm_ms_per_step / ms_per_step if ms_per_step else None,
+                         "eager_ms_per_step": eager_ms,
                          "step_model_tflops": flops_per_sample_step() * B / (ms_per_step * 1e-3) / 1e12},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -222,10 +222,24 @@ int mtvaf_combine_loss(const float* crf_nll_sum, int B, const float* prob_loss, 
 
 /* ---- optimizer: torch.optim.AdamW as configured in modules/train.py:887-926 ------------------- */
 /* zero_grad != 0 clears `grad` in the same pass (replaces optimizer.zero_grad()); bf16_copy (optional) receives
- * the updated weights rounded to bf16 (the tensor-core GEMM operands). */
+ * the updated weights rounded to bf16 (the tensor-core GEMM operands).  `dyn` (optional, device memory, 24 bytes:
+ * uint64 t; float lr_scale, bc1, bc2_sqrt -- maintained by mtvaf_adam_dyn_advance) overrides the by-value step:
+ * lr is multiplied by lr_scale and the bias corrections come from the device, so the call can be replayed from
+ * a CUDA graph. */
 int mtvaf_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                     void* bf16_copy, int zero_grad, void* stream);
+                     void* bf16_copy, int zero_grad, const void* dyn, void* stream);
+/* dyn->t += 1, then lr_scale = get_linear_schedule_with_warmup (modules/train.py:118-120) for that step
+ * (1.0 if total_steps <= 0) and the Adam bias corrections for t. */
+int mtvaf_adam_dyn_advance(void* dyn, float beta1, float beta2, int warmup_steps, int total_steps, void* stream);
+
+/* ---- CUDA-graph replay support -------------------------------------------------------------- */
+/* Registers a device-resident uint64 step counter (NULL to unregister).  Every dropout site of the library mixes
+ * it into its by-value seed, so a training step captured ONCE into a CUDA graph draws fresh dropout masks on every
+ * replay (forward and backward of one replay see the same value).  Host-side only: stores the pointer. */
+int mtvaf_set_step_source(const uint64_t* dev_step);
+/* *dev_step += 1 (stream-ordered; capture it at the head of the graph). */
+int mtvaf_advance_step(uint64_t* dev_step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ struct AttnArgs {
   int B, L, nh;
   float scale;
   uint32_t drop_thr; float drop_scale; unsigned long long seed;
+  const unsigned long long* step;
 };
 
 template <typename T>
@@ -133,7 +134,7 @@ attn_fwd_kernel(AttnArgs a, T* __restrict__ ctx, long long ld_ctx, float* __rest
       m[j] = mn;
       if (a.drop_thr) {
         const int q = q0 + warp * 4 + j;
-        const uint32_t rk = attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q);
+        const uint32_t rk = attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q);
         p0 = attn_drop_keep(rk, k0 + lane, a.drop_thr) ? p0 * a.drop_scale : 0.f;
         p1 = attn_drop_keep(rk, k0 + lane + 32, a.drop_thr) ? p1 * a.drop_scale : 0.f;
       }
@@ -282,7 +283,7 @@ attn_bwd_dq_kernel(AttnArgs a, const T* __restrict__ dctx, long long ld_d, const
       float d0 = dp[j][0], d1 = dp[j][1];
       if (a.drop_thr) {
         const int q = q0 + warp * 4 + j;
-        const uint32_t rk = attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q);
+        const uint32_t rk = attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q);
         d0 = attn_drop_keep(rk, k0 + lane, a.drop_thr) ? d0 * a.drop_scale : 0.f;
         d1 = attn_drop_keep(rk, k0 + lane + 32, a.drop_thr) ? d1 * a.drop_scale : 0.f;
       }
@@ -396,7 +397,7 @@ attn_bwd_dkv_kernel(AttnArgs a, const T* __restrict__ dctx, long long ld_d, cons
       float d = dp[j], pd = p;
       if (a.drop_thr) {
         const int q = q0 + lane, kk = kbase + warp * 4 + j;
-        const bool keep = attn_drop_keep(attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q), kk,
+        const bool keep = attn_drop_keep(attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q), kk,
                                          a.drop_thr);
         d = keep ? d * a.drop_scale : 0.f;
         pd = keep ? p * a.drop_scale : 0.f;
@@ -464,7 +465,7 @@ static int fill_args(AttnArgs* a, const void* qkv, int64_t ld_qkv, const void* k
   a->key_mask = reinterpret_cast<const long long*>(key_mask);
   a->B = B; a->L = L; a->nh = nh;
   a->scale = 1.0f / sqrtf((float)d);
-  a->drop_thr = 0; a->drop_scale = 1.f; a->seed = seed;
+  a->drop_thr = 0; a->drop_scale = 1.f; a->seed = seed; a->step = step_source();
   if (p_drop > 0.f) {
     MTVAF_REQUIRE(p_drop < 1.f, "attention: dropout p must be < 1");
     double t = (double)p_drop * 4294967296.0;

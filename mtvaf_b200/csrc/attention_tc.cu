@@ -145,9 +145,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     const float mx2 = fmaxf(sExch[row], sExch[128 + row]);   // finite: key 0 exists and S is finite
 
-    // ---- pass 2: P = exp2(x - max), row sum, dropout, bf16 P -> shared memory
+    // ---- pass 2: P = exp2(x - max), row sum, dropout, bf16 P -> shared memory.  With dropout the 1/(1-p) scale
+    // rides in the exponent (max - log2(scale)): P is born scaled, the row sum is corrected once at the end.
     const uint32_t rowkey =
-        a.drop_thr ? attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
+        a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
+    const float mxs = a.drop_thr ? mx2 - log2f(a.drop_scale) : mx2;
     float sum = 0.f;
     for (int u = half; u < units; u += 2) {
       const int c = u << 3;
@@ -156,16 +158,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
       const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
       const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      bool keep[8];
-      if (a.drop_thr) attn_drop_keep8(rowkey, c < a.P8 ? c : a.P + (c - a.P8), a.drop_thr, keep);
       tmem_ld_wait();
       float p[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        p[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sc2, mk[j] - mx2));
+        p[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sc2, mk[j] - mxs));
         sum += p[j];
-        if (a.drop_thr) p[j] = keep[j] ? p[j] * a.drop_scale : 0.f;
       }
+      if (a.drop_thr) attn_drop_apply8(rowkey, c < a.P8 ? c : a.P + (c - a.P8), a.drop_thr, p);
       uint4 w;
       w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
       w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
@@ -198,7 +198,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // tcgen05.ld is warp-collective (.sync.aligned): EVERY lane issues the loads (rows past L included,
     // never inside a divergent branch); only the global stores are predicated.
-    const float inv = 1.f / total;
+    // O = (sum_k keep_k P'_k V_k) / (sum_k P'_k / scale) with P' = scale * P
+    const float inv = a.drop_scale / total;
     const bool valid = q < a.L;
     {
       uint32_t r[32];
@@ -218,7 +219,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     if (valid && half == 0)
-      lse_out[((long long)b * a.nh + h) * a.L + q] = (mx2 + log2f(total)) * 0.6931471805599453f;
+      lse_out[((long long)b * a.nh + h) * a.L + q] = (mxs + log2f(total)) * 0.6931471805599453f;
     // TMEM reads done before the next item's MMAs overwrite S / O; orders sMask / sExch reuse
     tc_fence_before();
     __syncthreads();
@@ -270,7 +271,7 @@ int attn_tc_prepare(const void* qkv, int64_t ld_qkv, const void* kp, const void*
   a->N16 = (a->P8 + L + 15) / 16 * 16;
   a->B = B; a->nh = nh; a->key_mask = reinterpret_cast<const long long*>(key_mask);
   a->scale = 0.125f;
-  a->drop_thr = 0; a->drop_scale = 1.f; a->seed = seed;
+  a->drop_thr = 0; a->drop_scale = 1.f; a->seed = seed; a->step = step_source();
   if (p_drop > 0.f) {
     double t = (double)p_drop * 4294967296.0;
     a->drop_thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;

@@ -15,6 +15,7 @@ struct AttnTcArgs {
   const long long* key_mask;
   float scale;
   uint32_t drop_thr; float drop_scale; unsigned long long seed;
+  const unsigned long long* step;   // device step counter mixed into the seed (or NULL)
 };
 
 struct AttnTcMaps {

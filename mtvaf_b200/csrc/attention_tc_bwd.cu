@@ -10,13 +10,17 @@
 // models/bert_model.py:566-587) falls out of the same two MMAs as the text dK/dV.
 //
 // PERSISTENT: one CTA (512 threads) per SM walks the (batch, head) items; all L <= 128 queries x all P+L
-// keys of an item are resident.  Per item:
-//   TMA  : {Q, K_p, K} and {dO, V_p, V} on two mbarriers (S can start before dO/V land); the loads of the
-//          NEXT item are issued as soon as this item's last MMA has retired, i.e. they overlap the stores
+// keys of an item are resident.  The kernel is bound by the latency chain load -> MMA -> SIMT -> MMA -> store and
+// by ~130 KB of HBM traffic per item, so everything that can run ahead does:
+//   TMA  : {Q, K_p, K} are DOUBLE-buffered (when shared memory allows): the next item's tiles are requested at the
+//          top of the current item; V is requested as soon as dP = dO V^T has retired, dO as soon as the last MMA
+//          has retired (behind the stores); each has its own mbarrier, S starts as soon as Q/K are there
+//   regs : the next item's key-mask value, log-sum-exp and quarter row of O are fetched one item ahead
 //   MMA  : S -> TMEM cols [0,N16), dP -> TMEM cols [256,256+N16)          (both K-major operands)
 //   SIMT : thread = (query row, quarter of the 8-key units): rowsum(dO o O) from a quarter row of dO (smem)
-//          and O (global), exchanged through smem; S and dP from TMEM -> bf16 P and dS into shared memory in
-//          the K-major SWIZZLE_128B layout [q][64-key chunk] (one 16-byte piece per 8-key unit)
+//          and O (registers), exchanged through smem; S and dP from TMEM -> bf16 P and dS into shared memory in
+//          the K-major SWIZZLE_128B layout [q][64-key chunk] (one 16-byte piece per 8-key unit); the dropout
+//          scale rides in the exponent, the mask is one hash per PAIR of keys
 //   MMA  : dQ = dS K (A = dS K-major, B = K MN-major); dK = dS^T Q and dV = P^T dO per 128-key tile
 //          (A = the SAME dS / P buffers read as MN-major operands, B = Q / dO MN-major);
 //          accumulators alias the S / dP columns
@@ -31,22 +35,26 @@ constexpr int kBwdThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdSmem {
-  int n_chunks, kv_rows;
+  int n_chunks, kv_rows, nbuf;
   size_t off_ds, off_p, off_q, off_do, off_k, off_v, off_mask, off_exch, off_bar, total;
+  size_t q_stride, k_stride;
 };
 
-__host__ __device__ inline AttnBwdSmem attn_bwd_layout(int P8, int L64, int N16) {
+__host__ __device__ inline AttnBwdSmem attn_bwd_layout(int P8, int L64, int N16, int nbuf) {
   AttnBwdSmem s;
   s.n_chunks = (N16 + 63) / 64;
+  s.nbuf = nbuf;
   const int loaded = P8 + L64;
   s.kv_rows = loaded > N16 ? loaded : N16;
+  s.q_stride = 16384;
+  s.k_stride = (((size_t)s.kv_rows * 128) + 1023) / 1024 * 1024;
   size_t o = 0;
   s.off_ds = o; o += (size_t)s.n_chunks * 16384;      // dS chunks; a 128-key tile may read one chunk past
   s.off_p = o;  o += (size_t)s.n_chunks * 16384;      // the end (rows of the output that are never stored)
-  s.off_q = o;  o += 16384;
+  s.off_q = o;  o += s.q_stride * nbuf;
   s.off_do = o; o += 16384;
-  s.off_k = o;  o += (size_t)s.kv_rows * 128;
-  s.off_v = o;  o += (size_t)s.kv_rows * 128;
+  s.off_k = o;  o += s.k_stride * nbuf;
+  s.off_v = o;  o += s.k_stride;
   s.off_mask = o; o += (size_t)((N16 + 15) / 16) * 64;
   s.off_exch = o; o += 4 * 128 * sizeof(float);
   s.off_bar = o; o += 64;
@@ -54,26 +62,44 @@ __host__ __device__ inline AttnBwdSmem attn_bwd_layout(int P8, int L64, int N16)
   return s;
 }
 
+// 2 (double-buffered Q/K) when it fits in shared memory, else 1, else 0 (shape not supported)
+static int attn_bwd_pick_nbuf(const AttnTcArgs& a) {
+  if (attn_bwd_layout(a.P8, a.L64, a.N16, 2).total <= 227 * 1024) return 2;
+  if (attn_bwd_layout(a.P8, a.L64, a.N16, 1).total <= 227 * 1024) return 1;
+  return 0;
+}
+
+__device__ __forceinline__ float bwd_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmKp, const __grid_constant__ CUtensorMap tmVp,
-                   const __grid_constant__ CUtensorMap tmdO, AttnTcArgs a, const float* __restrict__ lse,
+                   const __grid_constant__ CUtensorMap tmdO, AttnTcArgs a, int nbuf, const float* __restrict__ lse,
                    const __nv_bfloat16* __restrict__ ctx, long long ld_ctx, __nv_bfloat16* __restrict__ dqkv,
                    long long ld_dqkv, float* __restrict__ dkp, float* __restrict__ dvp) {
   constexpr int DP_COL = 256;                          // TMEM column of dP (S at 0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const AttnBwdSmem lay = attn_bwd_layout(a.P8, a.L64, a.N16);
+  const AttnBwdSmem lay = attn_bwd_layout(a.P8, a.L64, a.N16, nbuf);
   uint8_t* sdS = smem + lay.off_ds;
   uint8_t* sP = smem + lay.off_p;
-  uint8_t* sQ = smem + lay.off_q;
+  uint8_t* sQ0 = smem + lay.off_q;
   uint8_t* sdO = smem + lay.off_do;
-  uint8_t* sK = smem + lay.off_k;
+  uint8_t* sK0 = smem + lay.off_k;
   uint8_t* sV = smem + lay.off_v;
   float* sMask = reinterpret_cast<float*>(smem + lay.off_mask);           // additive mask * log2(e)
   float* sExch = reinterpret_cast<float*>(smem + lay.off_exch);           // [4][128] partial rowsum(dO o O)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bar);       // q/k, dO/v, s/dp, grads
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bar);       // qk[0], qk[1], dO, V, s/dp, grads
+  uint64_t* bar_qk = bars;
+  uint64_t* bar_do = bars + 2;
+  uint64_t* bar_v = bars + 3;
+  uint64_t* bar_s = bars + 4;
+  uint64_t* bar_g = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;         // TMEM lane group / quarter of the columns
@@ -85,14 +111,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (tid == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmKV); prefetch_tmap(&tmdO);
     if (a.P8 > 0) { prefetch_tmap(&tmKp); prefetch_tmap(&tmVp); }
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   __syncwarp();
   if (warp == 0) tmem_alloc<512>(tmem_ptr);
   // K/V rows the TMA boxes do not cover but the MMAs read: zero them once (0 x garbage could be NaN)
   for (int i = loaded_rows * 8 + tid; i < a.N16 * 8; i += kBwdThreads) {
-    *reinterpret_cast<uint4*>(sK + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < nbuf; ++s) *reinterpret_cast<uint4*>(sK0 + s * lay.k_stride + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(sV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async_smem();
@@ -101,21 +127,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  auto issue_loads = [&](int item) {                   // one thread
+  const uint32_t kv_bytes = (uint32_t)loaded_rows * 128u;
+  auto load_qk = [&](int item, int buf) {              // one thread
     const int b = item / a.nh, h = item - b * a.nh;
-    const uint32_t bytes = 16384u + (uint32_t)loaded_rows * 128u;
-    mbar_arrive_expect_tx(&bars[0], bytes);
-    tma_load_2d(sQ, &tmQ, &bars[0], h * 64, b * a.L);
-    for (int r = 0; r < a.P8; r += 8) tma_load_2d(sK + r * 128, &tmKp, &bars[0], 0, (b * a.nh + h) * a.P + r);
+    uint8_t* q = sQ0 + buf * lay.q_stride;
+    uint8_t* k = sK0 + buf * lay.k_stride;
+    mbar_arrive_expect_tx(&bar_qk[buf], 16384u + kv_bytes);
+    tma_load_2d(q, &tmQ, &bar_qk[buf], h * 64, b * a.L);
+    for (int r = 0; r < a.P8; r += 8) tma_load_2d(k + r * 128, &tmKp, &bar_qk[buf], 0, (b * a.nh + h) * a.P + r);
     for (int r = 0; r < a.L64; r += 64)
-      tma_load_2d(sK + (a.P8 + r) * 128, &tmKV, &bars[0], H + h * 64, b * a.L + r);
-    mbar_arrive_expect_tx(&bars[1], bytes);
-    tma_load_2d(sdO, &tmdO, &bars[1], h * 64, b * a.L);
-    for (int r = 0; r < a.P8; r += 8) tma_load_2d(sV + r * 128, &tmVp, &bars[1], 0, (b * a.nh + h) * a.P + r);
-    for (int r = 0; r < a.L64; r += 64)
-      tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, &bars[1], 2 * H + h * 64, b * a.L + r);
+      tma_load_2d(k + (a.P8 + r) * 128, &tmKV, &bar_qk[buf], H + h * 64, b * a.L + r);
   };
-  if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
+  auto load_v = [&](int item) {
+    const int b = item / a.nh, h = item - b * a.nh;
+    mbar_arrive_expect_tx(bar_v, kv_bytes);
+    for (int r = 0; r < a.P8; r += 8) tma_load_2d(sV + r * 128, &tmVp, bar_v, 0, (b * a.nh + h) * a.P + r);
+    for (int r = 0; r < a.L64; r += 64)
+      tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, bar_v, 2 * H + h * 64, b * a.L + r);
+  };
+  auto load_do = [&](int item) {
+    const int b = item / a.nh, h = item - b * a.nh;
+    mbar_arrive_expect_tx(bar_do, 16384u);
+    tma_load_2d(sdO, &tmdO, bar_do, h * 64, b * a.L);
+  };
 
   const bool row_ok = row < a.L;
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -126,50 +160,81 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_tiles = (a.N16 + 127) / 128;             // 128-key tiles of dK / dV
   constexpr int DQ_COL = 0, DK_COL = 64, DV_COL = DP_COL;   // dK tiles at 64, 128 ; dV tiles at 256, 320
   const int dcol = part * 16;                          // this thread's 16 of the 64 head-dim columns
+  const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
+  const float ds_coef = a.scale / a.drop_scale;        // dS = P' * (scale / drop_scale) * (dP' - D)
 
-  uint32_t ph = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ph ^= 1) {
+  // per-item values fetched one item ahead: key-mask entry of key `tid`, log-sum-exp, quarter row of O
+  auto fetch_mask = [&](int item) -> float {
+    if (tid >= a.N16) return 0.f;
+    const int b = item / a.nh;
+    if (tid < a.P8) return (tid < a.P) ? 0.f : -INFINITY;
+    const int t = tid - a.P8;
+    return (t < a.L) ? (a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kLog2e) : -INFINITY;
+  };
+  auto fetch_lse = [&](int item) -> float {
     const int b = item / a.nh, h = item - b * a.nh;
-    // ---- key validity / additive mask (x log2 e) in smem-key numbering: 0 visible, -10000 padded text key,
-    //      -inf = no such key (prefix padding, rows past L)
-    for (int k = tid; k < a.N16; k += kBwdThreads) {
-      float m;
-      if (k < a.P8) m = (k < a.P) ? 0.f : -INFINITY;
-      else {
-        const int t = k - a.P8;
-        m = (t < a.L) ? (a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kLog2e) : -INFINITY;
-      }
-      sMask[k] = m;
-    }
-    // ---- per-row scalars and this thread's quarter row of O (global, 32 B)
-    const float lse2 = row_ok ? lse[((long long)b * a.nh + h) * a.L + row] * kLog2e : INFINITY;
-    uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+    // +inf for rows past L: P = exp2(-inf) = 0
+    return row_ok ? lse[((long long)b * a.nh + h) * a.L + row] * kLog2e - log2_ds : INFINITY;
+  };
+  auto fetch_o = [&](int item, uint4& o0, uint4& o1) {
+    o0 = make_uint4(0, 0, 0, 0);
+    o1 = o0;
     if (row_ok) {
+      const int b = item / a.nh, h = item - b * a.nh;
       const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)b * a.L + row) * ld_ctx + h * 64 + dcol);
       o0 = po[0];
       o1 = po[1];
     }
+  };
+
+  const int first = blockIdx.x;
+  float m_next = 0.f, lse_next = 0.f;
+  uint4 o0n = make_uint4(0, 0, 0, 0), o1n = o0n;
+  if (first < n_items) {
+    if (tid == 0) { load_qk(first, 0); load_do(first); load_v(first); }
+    m_next = fetch_mask(first);
+    lse_next = fetch_lse(first);
+    fetch_o(first, o0n, o1n);
+  }
+
+  int il = 0;                                          // local iteration count
+  for (int item = first; item < n_items; item += gridDim.x, ++il) {
+    const int b = item / a.nh, h = item - b * a.nh;
+    const int buf = nbuf == 2 ? (il & 1) : 0;
+    const uint32_t ph = il & 1;
+    const uint32_t ph_qk = nbuf == 2 ? ((il >> 1) & 1) : ph;
+    const int next = item + gridDim.x;
+    uint8_t* sQ = sQ0 + buf * lay.q_stride;
+    uint8_t* sK = sK0 + buf * lay.k_stride;
+    // ---- this item's prefetched scalars; key validity / additive mask (x log2 e) in smem-key numbering:
+    //      0 visible, -10000 padded text key, -inf = no such key (prefix padding, rows past L)
+    if (tid < a.N16) sMask[tid] = m_next;
+    const float lse2 = lse_next;
+    const uint4 o0 = o0n, o1 = o1n;
     if (tid == 0) {
+      // the other Q/K buffer was last read by the previous item's MMAs (retired): request the next item's tiles
+      if (nbuf == 2 && next < n_items) load_qk(next, buf ^ 1);
       // ---- S = Q K^T -> cols [0,N16) ; dP = dO V^T -> cols [256, 256+N16)
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), adO = smem_u32(sdO), aV = smem_u32(sV);
       const uint32_t idesc = make_idesc_bf16(128, a.N16, false, false);
-      mbar_wait(&bars[0], ph);
+      mbar_wait(&bar_qk[buf], ph_qk);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_f16_ss(tmem_base, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
                     make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-      mbar_wait(&bars[1], ph);
+      mbar_wait(bar_do, ph);
+      mbar_wait(bar_v, ph);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_f16_ss(tmem_base + DP_COL, make_smem_desc_sw128(adO + k * 32, 16, 1024),
                     make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-      umma_commit(&bars[2]);
+      umma_commit(bar_s);
     }
     __syncwarp();
     // ---- D_q = rowsum(dO o O): this thread's 16 columns (two 16-byte pieces of the swizzled dO row)
-    mbar_wait(&bars[1], ph);
+    mbar_wait(bar_do, ph);
     {
       const uint8_t* pd = sdO + prow_off;
       const uint4 d0 = *reinterpret_cast<const uint4*>(pd + (((part * 2) ^ row8) << 4));
@@ -188,13 +253,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();                                   // publishes sMask and sExch
     const float dsum = (sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row]);
     const uint32_t rowkey =
-        a.drop_thr ? attn_drop_rowkey(a.seed, ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
+        a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
+    // the next item's scalars travel while this item's softmax runs
+    if (next < n_items) {
+      m_next = fetch_mask(next);
+      lse_next = fetch_lse(next);
+      fetch_o(next, o0n, o1n);
+    }
 
-    mbar_wait(&bars[2], ph);
+    mbar_wait(bar_s, ph);
     __syncwarp();
     tc_fence_after();
+    if (tid == 0 && next < n_items) load_v(next);      // dP has retired: V is free
 
-    // ---- P and dS for this thread's (row, every 4th 8-key unit)
+    // ---- P and dS for this thread's (row, every 4th 8-key unit).  P' = P / (1-p) is born scaled (the dropout scale
+    // rides in the exponent: lse2 already carries -log2(scale)); dropped keys are zeroed in P' and in dP.
     for (int u = part; u < units; u += 4) {
       const int c = u << 3;
       uint32_t rs[8], rd[8];
@@ -203,23 +276,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
       const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
       const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      bool keep[8];
-      if (a.drop_thr) attn_drop_keep8(rowkey, c < a.P8 ? c : a.P + (c - a.P8), a.drop_thr, keep);
       tmem_ld_wait();
-      float p[8], ds[8];
+      float p[8], dp[8], ds[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         // masked / absent keys and rows past L give exp2(-inf) = 0 (S and dP are finite: padded K/V rows are 0)
-        const float pj = exp2f(fmaf(__uint_as_float(rs[j]), sc2, mk[j] - lse2));
-        float dp = __uint_as_float(rd[j]);
-        float pk = pj;
-        if (a.drop_thr) {
-          dp = keep[j] ? dp * a.drop_scale : 0.f;
-          pk = keep[j] ? pj * a.drop_scale : 0.f;
-        }
-        ds[j] = (pj * a.scale) * (dp - dsum);
-        p[j] = pk;
+        p[j] = bwd_ex2(fmaf(__uint_as_float(rs[j]), sc2, mk[j] - lse2));
+        dp[j] = __uint_as_float(rd[j]) * a.drop_scale;
+        ds[j] = p[j] * ds_coef;
       }
+      if (a.drop_thr) attn_drop_apply8(rowkey, c < a.P8 ? c : a.P + (c - a.P8), a.drop_thr, p, dp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ds[j] *= dp[j] - dsum;
       const uint32_t off = (u >> 3) * 16384 + prow_off + (((u & 7) ^ row8) << 4);
       uint4 w;
       w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
@@ -259,14 +327,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_f16_ss(tmem_base + DV_COL + t * 64, make_smem_desc_sw128(aP + t * 32768 + j * 2048, 16384, 1024),
                       make_smem_desc_sw128(adO + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1u : 0u);
       }
-      umma_commit(&bars[3]);
+      umma_commit(bar_g);
     }
     __syncwarp();
-    mbar_wait(&bars[3], ph);
+    mbar_wait(bar_g, ph);
     __syncwarp();
     tc_fence_after();
     // every operand tile of this item has been consumed: fetch the next item's while the gradients drain
-    if (tid == 0 && item + (int)gridDim.x < n_items) issue_loads(item + gridDim.x);
+    if (tid == 0 && next < n_items) {
+      load_do(next);
+      if (nbuf == 1) load_qk(next, 0);
+    }
     __syncwarp();
 
     // ---- stores: this thread owns 16 of the 64 head-dim columns of its row (TMEM loads are warp-collective:
@@ -339,7 +410,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // shape gate of the backward kernel (on top of attn_tc_prepare's)
 bool attn_bwd_tc_supported(const AttnTcArgs& a) {
   if (a.L > 128 || a.N16 > 256) return false;
-  return attn_bwd_layout(a.P8, a.L64, a.N16).total <= 227 * 1024;
+  return attn_bwd_pick_nbuf(a) > 0;
 }
 
 int attn_bwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
@@ -354,7 +425,9 @@ int attn_bwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dct
   const uint64_t H = (uint64_t)a.nh * 64;
   int rc = make_tmap_bf16_2d(&tmdO, dctx, H, T, ld_dctx, 64, 128);
   if (rc) return rc;
-  const AttnBwdSmem lay = attn_bwd_layout(a.P8, a.L64, a.N16);
+  const int nbuf = attn_bwd_pick_nbuf(a);
+  MTVAF_REQUIRE(nbuf > 0, "attention_bwd(tc): shape does not fit in shared memory");
+  const AttnBwdSmem lay = attn_bwd_layout(a.P8, a.L64, a.N16, nbuf);
   static bool set = false;
   if (!set) {
     MTVAF_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -362,7 +435,7 @@ int attn_bwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dct
   }
   const int n_items = a.B * a.nh;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  attn_bwd_tc_kernel<<<grid, kBwdThreads, lay.total, st>>>(m.q, m.kv, m.kp, m.vp, tmdO, a, lse,
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, lay.total, st>>>(m.q, m.kv, m.kp, m.vp, tmdO, a, nbuf, lse,
                                                           (const __nv_bfloat16*)ctx, ld_ctx, (__nv_bfloat16*)dqkv,
                                                           ld_dqkv, dkp, dvp);
   MTVAF_LAUNCH_CHECK();

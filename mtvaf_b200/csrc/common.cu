@@ -16,6 +16,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static const unsigned long long* g_step_source = nullptr;   // see mtvaf_set_step_source
+const unsigned long long* step_source() { return g_step_source; }
+void set_step_source(const unsigned long long* p) { g_step_source = p; }
+
 static std::atomic<unsigned long long> g_launches{0};   // statistics only: kernels launched by this library
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -32,6 +36,10 @@ int sm_count() {
 }  // namespace mtvaf
 
 extern "C" int mtvaf_abi_version(void) { return MTVAF_ABI_VERSION; }
+extern "C" int mtvaf_set_step_source(const uint64_t* dev_step) {
+  mtvaf::set_step_source(reinterpret_cast<const unsigned long long*>(dev_step));
+  return 0;
+}
 extern "C" uint64_t mtvaf_launch_count(void) { return mtvaf::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* mtvaf_last_error(void) { return mtvaf::g_last_error; }
 extern "C" int mtvaf_device_info(int* sm_count, int* cc_major, int* cc_minor) {

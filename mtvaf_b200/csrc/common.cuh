@@ -34,6 +34,9 @@ void note_launch();
   } while (0)
 
 int sm_count();
+// device pointer registered with mtvaf_set_step_source (or NULL): a step counter in HBM that every dropout site
+// mixes into its seed, so a CUDA graph captured once draws fresh masks on every replay
+const unsigned long long* step_source();
 
 // ---- element type helpers -----------------------------------------------------------------------
 template <typename T>
@@ -184,6 +187,10 @@ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
   h = (h ^ (hi * 0x85EBCA77u + s1)) * 0xC2B2AE3Du;
   return h;
 }
+// effective seed of a dropout site: the by-value seed plus the device-resident step counter (if registered)
+__device__ __forceinline__ unsigned long long step_seed(unsigned long long seed, const unsigned long long* step) {
+  return step ? seed + (*step) * 0x9E3779B97F4A7C15ull : seed;
+}
 // threshold = round(p * 2^32) (clamped); element is KEPT iff bits >= threshold
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
   return dropout_bits(seed, idx) >= threshold;
@@ -208,21 +215,37 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int kk, uint32_t
   attn_drop_pair(rowkey, static_cast<uint32_t>(kk) >> 1, h0, h1);
   return ((kk & 1) ? h1 : h0) >= thr;
 }
-// keep flags of the 8 consecutive keys kk0 .. kk0+7 (kk0 >= 0)
-__device__ __forceinline__ void attn_drop_keep8(uint32_t rowkey, int kk0, uint32_t thr, bool (&keep)[8]) {
+// zero the dropped entries among the 8 consecutive keys kk0 .. kk0+7 (kk0 >= 0) of v (and w): the hash of a pair
+// is consumed as predicates right away (no flag array in registers); the 1/(1-p) scale is the caller's business
+__device__ __forceinline__ void attn_drop_apply8(uint32_t rowkey, int kk0, uint32_t thr, float (&v)[8]) {
   if ((kk0 & 1) == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t h0, h1;
       attn_drop_pair(rowkey, static_cast<uint32_t>(kk0 >> 1) + i, h0, h1);
-      keep[2 * i] = h0 >= thr;
-      keep[2 * i + 1] = h1 >= thr;
+      if (h0 < thr) v[2 * i] = 0.f;
+      if (h1 < thr) v[2 * i + 1] = 0.f;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) keep[j] = attn_drop_keep(rowkey, kk0 + j, thr);
+    for (int j = 0; j < 8; ++j)
+      if (!attn_drop_keep(rowkey, kk0 + j, thr)) v[j] = 0.f;
   }
 }
-
+__device__ __forceinline__ void attn_drop_apply8(uint32_t rowkey, int kk0, uint32_t thr, float (&v)[8], float (&w)[8]) {
+  if ((kk0 & 1) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t h0, h1;
+      attn_drop_pair(rowkey, static_cast<uint32_t>(kk0 >> 1) + i, h0, h1);
+      if (h0 < thr) { v[2 * i] = 0.f; w[2 * i] = 0.f; }
+      if (h1 < thr) { v[2 * i + 1] = 0.f; w[2 * i + 1] = 0.f; }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!attn_drop_keep(rowkey, kk0 + j, thr)) { v[j] = 0.f; w[j] = 0.f; }
+  }
+}
 
 }  // namespace mtvaf

@@ -154,7 +154,9 @@ __global__ void mean4_bwd_kernel(const float* __restrict__ dy, float* __restrict
 // ------------------------------------------------------------------ dropout apply / accumulate
 template <typename T>
 __global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, uint32_t thr,
-                                     float scale, unsigned long long seed) {
+                                     float scale, unsigned long long seed_in,
+                                     const unsigned long long* __restrict__ step) {
+  const unsigned long long seed = step_seed(seed_in, step);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = dropout_keep(seed, (unsigned long long)i, thr) ? from_f<T>(to_f<T>(x[i]) * scale) : from_f<T>(0.f);
@@ -215,6 +217,25 @@ __global__ void combine_loss_kernel(const float* crf_nll_sum, float inv_b, const
 }
 
 // ------------------------------------------------------------------ AdamW (torch.optim.AdamW semantics)
+// device-resident optimizer clock (CUDA-graph replay: nothing that changes per step may be a kernel argument)
+struct AdamDyn { unsigned long long t; float lr_scale; float bc1; float bc2_sqrt; };
+// t += 1; linear warm-up / linear decay factor of get_linear_schedule_with_warmup evaluated for the step about to
+// be taken (modules/train.py:118-120,919-921) and the two Adam bias corrections
+__global__ void adam_dyn_advance_kernel(AdamDyn* d, float b1, float b2, int warmup, int total) {
+  const unsigned long long s = d->t;              // steps taken so far
+  const unsigned long long t = s + 1;
+  float scale = 1.f;
+  if (total > 0) {
+    if ((long long)s < warmup) scale = (float)s / fmaxf(1.f, (float)warmup);
+    else scale = fmaxf(0.f, (float)((long long)total - (long long)s) / fmaxf(1.f, (float)(total - warmup)));
+  }
+  d->t = t;
+  d->lr_scale = scale;
+  d->bc1 = 1.f - powf(b1, (float)t);
+  d->bc2_sqrt = sqrtf(1.f - powf(b2, (float)t));
+}
+__global__ void advance_step_kernel(unsigned long long* p) { *p += 1ull; }
+
 __device__ __forceinline__ void adamw_one(float& w, float g, float& m, float& v, float lr, float b1, float b2,
                                           float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
   const float grad = g * gscale;
@@ -230,7 +251,8 @@ __device__ __forceinline__ void adamw_one(float& w, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
              float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
-             __nv_bfloat16* __restrict__ bf, int zero_grad) {
+             __nv_bfloat16* __restrict__ bf, int zero_grad, const AdamDyn* __restrict__ dyn) {
+  if (dyn) { lr *= dyn->lr_scale; bc1 = dyn->bc1; bc2_sqrt = dyn->bc2_sqrt; }
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -266,7 +288,8 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
 __global__ void adamw_scalar_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                     float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                     float wd, float bc1, float bc2_sqrt, float gscale, __nv_bfloat16* __restrict__ bf,
-                                    int zero_grad) {
+                                    int zero_grad, const AdamDyn* __restrict__ dyn) {
+  if (dyn) { lr *= dyn->lr_scale; bc1 = dyn->bc1; bc2_sqrt = dyn->bc2_sqrt; }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float w = p[i], mi = m[i], vi = v[i];
@@ -309,10 +332,10 @@ extern "C" int mtvaf_dropout_apply(const void* x, void* y, int64_t n, int dtype,
   const float scale = 1.f / (1.f - p_drop);
   if (dtype == MTVAF_BF16)
     dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, thr, scale, seed);
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, thr, scale, seed, step_source());
   else
     dropout_apply_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, n, thr,
-                                                                                    scale, seed);
+                                                                                    scale, seed, step_source());
   MTVAF_LAUNCH_CHECK();
   return 0;
 }
@@ -427,22 +450,39 @@ extern "C" int mtvaf_combine_loss(const float* crf_nll_sum, int B, const float* 
 
 extern "C" int mtvaf_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                                float grad_scale, void* bf16_copy, int zero_grad, void* stream) {
+                                float grad_scale, void* bf16_copy, int zero_grad, const void* dyn, void* stream) {
   if (n <= 0) return 0;
-  MTVAF_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "adamw: bad argument");
+  MTVAF_REQUIRE(param && grad && exp_avg && exp_avg_sq && (step >= 1 || dyn), "adamw: bad argument");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
   const bool vec = al(param, 16) && al(grad, 16) && al(exp_avg, 16) && al(exp_avg_sq, 16) &&
                    (!bf16_copy || al(bf16_copy, 8));
+  const AdamDyn* d = static_cast<const AdamDyn*>(dyn);
   if (vec)
     adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale,
-        (__nv_bfloat16*)bf16_copy, zero_grad);
+        (__nv_bfloat16*)bf16_copy, zero_grad, d);
   else
     adamw_scalar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale,
-        (__nv_bfloat16*)bf16_copy, zero_grad);
+        (__nv_bfloat16*)bf16_copy, zero_grad, d);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_adam_dyn_advance(void* dyn, float beta1, float beta2, int warmup_steps, int total_steps,
+                                      void* stream) {
+  MTVAF_REQUIRE(dyn && reinterpret_cast<uintptr_t>(dyn) % 8 == 0, "adam_dyn_advance: bad pointer");
+  adam_dyn_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<AdamDyn*>(dyn), beta1, beta2, warmup_steps,
+                                                             total_steps);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_advance_step(uint64_t* dev_step, void* stream) {
+  MTVAF_REQUIRE(dev_step, "advance_step: null pointer");
+  advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(dev_step));
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -26,6 +26,7 @@ struct EpiArgs {
   uint32_t drop_threshold;   // 0 = no dropout
   float drop_scale;          // 1/(1-p)
   unsigned long long seed;
+  const unsigned long long* step;   // device step counter mixed into the seed (or NULL)
 };
 
 inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N, int splits, EpiArgs* o) {
@@ -36,6 +37,7 @@ inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N
   o->out2 = e.out2; o->ld_out2 = e.ld_out2; o->rowvec = e.rowvec;
   o->alpha = (e.alpha == 0.f) ? 1.f : e.alpha;
   o->seed = e.seed;
+  o->step = step_source();
   o->drop_threshold = 0; o->drop_scale = 1.f;
   MTVAF_REQUIRE(e.mode >= 0 && e.mode <= MTVAF_EPI_ROWSCALE, "bad epilogue mode %d", e.mode);
   if (e.mode == MTVAF_EPI_ATOMIC_F32) o->out_bf16 = 0;
@@ -62,6 +64,15 @@ inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N
               al(o->out2, o->ld_out2, o->out_bf16) && (!o->bias || reinterpret_cast<uintptr_t>(o->bias) % 16 == 0);
   o->staged = o->vec_ok && o->out_bf16 && o->out != nullptr && (!o->aux || o->aux_bf16) && splits <= 1;
   return 0;
+}
+
+// kernels call this once at entry: folds the device step counter into the by-value seed (one global load per
+// thread instead of one per element)
+__device__ __forceinline__ EpiArgs resolve_step(const EpiArgs& in) {
+  EpiArgs e = in;
+  if (in.drop_threshold) e.seed = step_seed(in.seed, in.step);
+  e.step = nullptr;
+  return e;
 }
 
 __device__ __forceinline__ float epi_load(const void* p, int bf16, long long idx) {

@@ -64,7 +64,8 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ G, long long
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(S_THREADS)
 gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int M, int N,
-                int K, int k_per_split, EpiArgs ep, int a_vec, int b_vec) {
+                int K, int k_per_split, EpiArgs ep_in, int a_vec, int b_vec) {
+  const EpiArgs ep = resolve_step(ep_in);
   __shared__ __align__(16) float As[2][SB_K][SB_M + 4];
   __shared__ __align__(16) float Bs[2][SB_K][SB_N + 4];
   const int m0 = blockIdx.y * SB_M, n0 = blockIdx.x * SB_N;

@@ -52,7 +52,8 @@ __device__ __forceinline__ WorkItem decode_item(int item, int n_tiles_n, int n_t
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const EpiArgs ep, int M, int N, int K, int splits, int kb_per) {
+                    const EpiArgs ep_in, int M, int N, int K, int splits, int kb_per) {
+  const EpiArgs ep = resolve_step(ep_in);
   using namespace ptx;
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];

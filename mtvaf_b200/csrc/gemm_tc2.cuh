@@ -100,8 +100,9 @@ template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                     const __grid_constant__ CUtensorMap tmAux, const EpiArgs ep, int M, int N, int K, int splits,
+                     const __grid_constant__ CUtensorMap tmAux, const EpiArgs ep_in, int M, int N, int K, int splits,
                      int kb_per) {
+  const EpiArgs ep = resolve_step(ep_in);
   using namespace ptx;
   using S = Gemm2Smem<BN, EPI>;
   using SE = StagedEpi<EPI>;

@@ -131,7 +131,9 @@ template <typename TO, typename TM>
 __global__ void __launch_bounds__(256)
 prompt_grad_combine_kernel(const float* __restrict__ d_guids, const float* __restrict__ d_gs,
                            const TM* __restrict__ d_gm, long long rows, int W, TO* __restrict__ out,
-                           uint32_t drop_thr, float drop_scale, unsigned long long seed) {
+                           uint32_t drop_thr, float drop_scale, unsigned long long seed_in,
+                           const unsigned long long* __restrict__ step) {
+  const unsigned long long seed = drop_thr ? step_seed(seed_in, step) : seed_in;
   const int S = W / 4;
   const long long n8 = rows * 4 * (W / 8);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -486,7 +488,7 @@ extern "C" int mtvaf_prompt_grad_combine(const float* d_guids, const float* d_gs
   cudaStream_t st = (cudaStream_t)stream;
 #define MTVAF_PGC(TO_, TM_)                                                                                       \
   prompt_grad_combine_kernel<TO_, TM_><<<(int)blocks, 256, 0, st>>>(d_guids, d_gs, (const TM_*)d_gm, rows, W,    \
-                                                                    (TO_*)out, thr, scale, seed)
+                                                                    (TO_*)out, thr, scale, seed, step_source())
   const bool ob = out_dtype == MTVAF_BF16, mb = gm_dtype == MTVAF_BF16;
   if (ob && mb) MTVAF_PGC(__nv_bfloat16, __nv_bfloat16);
   else if (ob) MTVAF_PGC(__nv_bfloat16, float);

@@ -87,9 +87,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NV <= 3 && sizeof(T) == 2) ? 3
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int rows, int H,
                      T* __restrict__ dz, T* __restrict__ dd, float* __restrict__ d_gamma, float* __restrict__ d_beta,
-                     float* __restrict__ d_bias, uint32_t drop_thr, float drop_scale, unsigned long long seed) {
+                     float* __restrict__ d_bias, uint32_t drop_thr, float drop_scale, unsigned long long seed_in,
+                     const unsigned long long* __restrict__ step) {
   __shared__ float red[LN_WARPS * 256];
   using V = Vec8<T>;
+  const unsigned long long seed = drop_thr ? step_seed(seed_in, step) : seed_in;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[NV][8], ab[NV][8], ac[NV][8];
 #pragma unroll
@@ -211,10 +213,12 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
                     const float* __restrict__ word, const float* __restrict__ pemb, const float* __restrict__ temb,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int H,
                     T* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                    uint32_t drop_thr, float drop_scale, unsigned long long seed) {
+                    uint32_t drop_thr, float drop_scale, unsigned long long seed_in,
+                    const unsigned long long* __restrict__ step) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const unsigned long long seed = drop_thr ? step_seed(seed_in, step) : seed_in;
   const float* w = word + ids[row] * (long long)H;
   const float* p = pemb + pos[row] * (long long)H;
   const float* t = temb + tts[row] * (long long)H;
@@ -275,10 +279,11 @@ embed_ln_bwd_kernel(const T* __restrict__ dout, const int64_t* __restrict__ ids,
                     const float* __restrict__ rstd_in, int B, int L, int H, int word_pad, int pos_pad,
                     float* __restrict__ d_word, float* __restrict__ d_pos, float* __restrict__ d_type,
                     float* __restrict__ d_gamma, float* __restrict__ d_beta, uint32_t drop_thr, float drop_scale,
-                    unsigned long long seed) {
+                    unsigned long long seed_in, const unsigned long long* __restrict__ step) {
   __shared__ float red[LN_WARPS * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = B * L;
+  const unsigned long long seed = drop_thr ? step_seed(seed_in, step) : seed_in;
   float ag[NV][8], ab[NV][8], ade[NV][8], aw[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -425,7 +430,8 @@ static int launch_ln_bwd(const void* dy, const void* z, const float* gamma, cons
   if (grid > cap) grid = cap;
 #define MTVAF_LN_BWD(NV_)                                                                                          \
   layernorm_bwd_kernel<T, NV_><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)z, gamma, mean, rstd, rows, H, \
-                                                              (T*)dz, (T*)dd, d_gamma, d_beta, d_bias, thr, scale, seed)
+                                                              (T*)dz, (T*)dd, d_gamma, d_beta, d_bias, thr, scale, seed, \
+                                                              step_source())
   if (nv == 1) MTVAF_LN_BWD(1);
   else if (nv == 2) MTVAF_LN_BWD(2);
   else if (nv == 3) MTVAF_LN_BWD(3);
@@ -473,11 +479,11 @@ extern "C" int mtvaf_embed_ln_fwd(const int64_t* input_ids, const int64_t* token
     embed_ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, st>>>(input_ids, token_type_ids, position_ids,
                                                                       word_emb, pos_emb, type_emb, gamma, beta, eps,
                                                                       rows, H, (__nv_bfloat16*)out, mean, rstd, thr,
-                                                                      scale, seed);
+                                                                      scale, seed, step_source());
   else
     embed_ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>(input_ids, token_type_ids, position_ids, word_emb,
                                                               pos_emb, type_emb, gamma, beta, eps, rows, H,
-                                                              (float*)out, mean, rstd, thr, scale, seed);
+                                                              (float*)out, mean, rstd, thr, scale, seed, step_source());
   MTVAF_LAUNCH_CHECK();
   return 0;
 }
@@ -505,7 +511,7 @@ extern "C" int mtvaf_embed_ln_bwd(const void* dout, int dtype, const int64_t* in
 #define MTVAF_EMB_BWD(T_, NV_)                                                                                      \
   embed_ln_bwd_kernel<T_, NV_><<<grid, LN_WARPS * 32, 0, st>>>((const T_*)dout, input_ids, token_type_ids,           \
       position_ids, word_emb, pos_emb, type_emb, gamma, mean, rstd, B, L, H, word_pad, pos_pad, d_word, d_pos,      \
-      d_type, d_gamma, d_beta, thr, scale, seed)
+      d_type, d_gamma, d_beta, thr, scale, seed, step_source())
   if (dtype == MTVAF_BF16) {
     if (nv == 1) MTVAF_EMB_BWD(__nv_bfloat16, 1); else if (nv == 2) MTVAF_EMB_BWD(__nv_bfloat16, 2);
     else if (nv == 3) MTVAF_EMB_BWD(__nv_bfloat16, 3); else MTVAF_EMB_BWD(__nv_bfloat16, 4);

@@ -66,7 +66,10 @@ SIGNATURES = {
     "mtvaf_crf_nll_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
     "mtvaf_crf_decode": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtvaf_combine_loss": [_vp, _i, _vp, _f, _i, _vp, _i, _f, _vp, _vp, _vp],
-    "mtvaf_adamw_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i, _vp],
+    "mtvaf_adamw_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i, _vp, _vp],
+    "mtvaf_adam_dyn_advance": [_vp, _f, _f, _i, _i, _vp],
+    "mtvaf_set_step_source": [_vp],
+    "mtvaf_advance_step": [_vp, _vp],
 }
 
 

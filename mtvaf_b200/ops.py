@@ -409,7 +409,25 @@ def combine_loss(crf_nll_sum, B, prob_loss, beta, epoch, img_losses, alpha):
     return out, flag
 
 
-def adamw_step(param, grad, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0, bf16_copy=None, zero_grad=False):
+def adamw_step(param, grad, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0, bf16_copy=None, zero_grad=False,
+               dyn=None):
     _check(_raw.mtvaf_adamw_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), lr, b1,
-                                 b2, eps, wd, step, grad_scale, _p(bf16_copy), int(zero_grad), _stream()),
+                                 b2, eps, wd, step, grad_scale, _p(bf16_copy), int(zero_grad), _p(dyn), _stream()),
            "adamw_step")
+
+
+def adam_dyn_advance(dyn, b1, b2, warmup_steps, total_steps):
+    """dyn: device int64[3] buffer (24 bytes) holding {uint64 t; float lr_scale, bc1, bc2_sqrt}."""
+    _check(_raw.mtvaf_adam_dyn_advance(dyn.data_ptr(), b1, b2, int(warmup_steps), int(total_steps), _stream()),
+           "adam_dyn_advance")
+
+
+def set_step_source(t: Optional[torch.Tensor]):
+    """Register (or clear) the device step counter every dropout site mixes into its seed (CUDA-graph replay)."""
+    if t is not None:
+        assert t.is_cuda and t.dtype == torch.int64 and t.numel() == 1
+    _check(_raw.mtvaf_set_step_source(_p(t)), "set_step_source")
+
+
+def advance_step(t: torch.Tensor):
+    _check(_raw.mtvaf_advance_step(t.data_ptr(), _stream()), "advance_step")

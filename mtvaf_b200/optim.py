@@ -56,6 +56,17 @@ class FlatAdamW:
         self.m = torch.zeros(f.total, dtype=F32, device=f.device)
         self.v = torch.zeros(f.total, dtype=F32, device=f.device)
         self.t = 0
+        self.dyn: Optional[torch.Tensor] = None    # device clock {uint64 t; float lr_scale, bc1, bc2_sqrt}
+
+    def enable_device_clock(self):
+        """Keep the step count, the learning-rate schedule factor and the Adam bias corrections in device memory
+        (advanced by one tiny kernel per step) so that `step()` issues identical launches every time -- the form
+        a CUDA graph can replay (mtvaf_b200.graph.GraphedTrainStep)."""
+        if self.dyn is None:
+            f = self.engine.flat
+            self.dyn = torch.zeros(3, dtype=torch.int64, device=f.device)
+            self.dyn[0] = self.t                   # steps taken so far (floats are rewritten by the advance kernel)
+        return self.dyn
 
     def lr_scale(self) -> float:
         """get_linear_schedule_with_warmup evaluated for the step about to be taken."""
@@ -73,13 +84,17 @@ class FlatAdamW:
         f = self.engine.flat
         scale = self.lr_scale()
         self.t += 1
+        if self.dyn is not None:
+            # device clock: t, lr factor and bias corrections are advanced on the GPU; kernel arguments stay constant
+            ops.adam_dyn_advance(self.dyn, self.betas[0], self.betas[1], self.warmup_steps, self.total_steps)
+            scale = 1.0
         bf = self.engine.bf16 and f.Wb is not None
         for a, b, lr, wd in self.ranges:
             shadow = None
             if bf and b <= f.cast_end:
                 shadow = f.Wb[a:b]
             ops.adamw_step(f.W[a:b], f.G[a:b], self.m[a:b], self.v[a:b], lr * scale, self.betas[0], self.betas[1],
-                           self.eps, wd, self.t, grad_scale, shadow, zero_grad)
+                           self.eps, wd, self.t, grad_scale, shadow, zero_grad, self.dyn)
         if zero_grad:
             for a, b in self._gaps():
                 f.G[a:b].zero_()

@@ -225,7 +225,8 @@ def test_layernorm_bwd_fused_dropout_and_bias_grad(ops, dtype, p_drop):
     dz_plain, same = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg0, db0)
     assert same is dz_plain
     dz, dd = ops.layernorm_bwd(dy, z, gamma, mean, rstd, dg, db, d_bias=dbias, p_drop=p_drop, seed=77)
-    assert torch.equal(dz, dz_plain) and torch.equal(dg, dg0) and torch.equal(db, db0)
+    assert torch.equal(dz, dz_plain)
+    assert rel_err(dg, dg0) < 1e-5 and rel_err(db, db0) < 1e-5     # atomics across blocks: order varies
     if p_drop > 0:
         keep = ops.dropout_apply(torch.ones(rows, H, device=DEV, dtype=dtype), p_drop, 77).float() > 0
         want = torch.where(keep, dz.float() / (1 - p_drop), torch.zeros((), device=DEV))
