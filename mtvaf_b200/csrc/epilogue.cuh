@@ -144,9 +144,10 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t
         v[j] = epi_math<MODE>(ep, v[j], needs_aux ? a[j] : 0.f, row, c + j, N, pre[j]);
       }
       if (mode == MTVAF_EPI_ATOMIC_F32) {
+        // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the scalar atomics' instruction count
         float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + c;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+        atomicAdd(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(reinterpret_cast<float4*>(o + 4), make_float4(v[4], v[5], v[6], v[7]));
       } else {
         if (mode == MTVAF_EPI_SQNORM) {
 #pragma unroll

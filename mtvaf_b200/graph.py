@@ -48,7 +48,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):      # same stream as the warm-up: no stale node streams
             self.loss = self._step()
         self.kernels_per_replay = ops.launch_count() - n0     # library kernels captured (NCCL / copies not counted)
         self.replays = 0

@@ -147,6 +147,21 @@ def _init_like_reference(module: nn.Module, std: float):
 # =================================================================================================
 # autograd bridges
 # =================================================================================================
+_ANCHORS = {}
+
+
+def _grad_anchor(like: torch.Tensor) -> torch.Tensor:
+    """Autograd anchor of the hand-written Functions: a HOST leaf that requires grad iff `like` (a representative
+    parameter) does.  The Functions write parameter gradients straight into the flat buffer, so they need some
+    differentiable input to be scheduled at all; a CUDA parameter in that role drags its cached AccumulateGrad
+    node -- and the stream it was first used on -- into every later backward, which breaks CUDA-graph capture
+    on another stream ("dependency created on uncaptured work").  A host tensor carries no stream."""
+    key = bool(like.requires_grad)
+    if key not in _ANCHORS:
+        _ANCHORS[key] = torch.zeros(1, requires_grad=key)
+    return _ANCHORS[key]
+
+
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine: Engine, ids, tts, mask, training, want_probs, embeds, anchor, kv):
@@ -318,7 +333,7 @@ class _EncoderModelBase(nn.Module):
         return self._engine
 
     def _anchor(self) -> torch.Tensor:
-        return self.embeddings.LayerNorm.weight
+        return _grad_anchor(self.embeddings.LayerNorm.weight)
 
     # -- reference API ----------------------------------------------------------------------------
     def _pack_prefix(self, past_key_values, B, eng: Engine):
@@ -715,7 +730,7 @@ class TVNetSAModel2(nn.Module):
         il = None
         if vao:
             il = imagelabel.to(device=feats.device, dtype=F32).contiguous()
-        kv, img_losses = _FusionFn.apply(eng, feats, il, vao, self.training, 3, self.fc.weight)
+        kv, img_losses = _FusionFn.apply(eng, feats, il, vao, self.training, 3, _grad_anchor(self.fc.weight))
         self._img_losses = img_losses if vao else None
         if vao:
             return kv, img_losses[0], [img_losses[j] for j in range(1, img_losses.numel())]
