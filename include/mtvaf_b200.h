@@ -89,6 +89,14 @@ int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, in
 int mtvaf_skinny_linear_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int M, int N,
                             int K, float* out, int64_t ldo, void* stream);
 
+/* backward of the skinny layer (N <= 16).  dgrad: dx[m,k] = keep(seed, m*K+k)/(1-p) * sum_n dy[m,n] w[n,k], i.e. with
+ * the dropout that precedes the tag head (bert_model.py:506) applied to the result, written as dx_dtype;
+ * wgrad: dw[n,k] += sum_m dy[m,n] x[m,k] (fp32 atomics), N*K/8 <= 1536. */
+int mtvaf_skinny_linear_dgrad(const float* dy, int64_t lddy, const float* w, int64_t ldw, int M, int N, int K,
+                              float p_drop, uint64_t seed, void* dx, int64_t lddx, int dx_dtype, void* stream);
+int mtvaf_skinny_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, int M, int N, int K,
+                              float* dw, int64_t lddw, void* stream);
+
 /* ---- elementwise / reductions --------------------------------------------------------------- */
 int mtvaf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int mtvaf_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);

@@ -157,6 +157,98 @@ skinny_linear_kernel(const float* __restrict__ x, long long ldx, const float* __
   }
 }
 
+// backward of the skinny layer, data gradient with the INPUT dropout of the head fused in (bert_model.py:506):
+//   dx[m, k] = keep(seed, m*K + k) / (1-p) * sum_n dy[m, n] w[n, k]      written in the encoder's compute dtype
+// warp per row, lanes own float4 pieces of K, W (N x K fp32, L1-resident) is streamed once per row.
+template <typename TO, int NT>
+__global__ void __launch_bounds__(256)
+skinny_dgrad_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ w, long long ldw, int M,
+                    int N, int K, TO* __restrict__ dx, long long lddx, uint32_t drop_thr, float drop_scale,
+                    unsigned long long seed_in, const unsigned long long* __restrict__ step) {
+  const unsigned long long seed = drop_thr ? step_seed(seed_in, step) : seed_in;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+    float g[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) g[n] = n < N ? dy[(long long)m * lddy + n] : 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (n < N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(w + (long long)n * ldw + k));
+          acc.x = fmaf(g[n], b.x, acc.x); acc.y = fmaf(g[n], b.y, acc.y);
+          acc.z = fmaf(g[n], b.z, acc.z); acc.w = fmaf(g[n], b.w, acc.w);
+        }
+      }
+      if (drop_thr) {
+        const unsigned long long i0 = (unsigned long long)m * K + k;
+        acc.x = dropout_keep(seed, i0 + 0, drop_thr) ? acc.x * drop_scale : 0.f;
+        acc.y = dropout_keep(seed, i0 + 1, drop_thr) ? acc.y * drop_scale : 0.f;
+        acc.z = dropout_keep(seed, i0 + 2, drop_thr) ? acc.z * drop_scale : 0.f;
+        acc.w = dropout_keep(seed, i0 + 3, drop_thr) ? acc.w * drop_scale : 0.f;
+      }
+      TO* o = dx + (long long)m * lddx + k;
+      if constexpr (sizeof(TO) == 4) {
+        *reinterpret_cast<float4*>(o) = acc;
+      } else {
+        uint2 u;
+        u.x = pack_bf16x2(acc.x, acc.y);
+        u.y = pack_bf16x2(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(o) = u;
+      }
+    }
+  }
+}
+
+// weight gradient of the skinny layer: dw[n, k] += sum_m dy[m, n] x[m, k].  Each thread owns up to PPT
+// (n, 8-wide k vector) pairs and walks the block's rows; x vectors are shared through L1 by the N threads of a
+// k vector, dy entries are warp-broadcast loads.  One fp32 atomic per element and block at the end.
+template <int PPT>
+__global__ void __launch_bounds__(256)
+skinny_wgrad_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx, int M,
+                    int N, int K, float* __restrict__ dw, long long lddw) {
+  const int kv = K >> 3;
+  const int pairs = N * kv;
+  float acc[PPT][8];
+  int pn[PPT], pk[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    const int id = threadIdx.x + p * 256;
+    pn[p] = id < pairs ? id / kv : -1;
+    pk[p] = id < pairs ? (id - (id / kv) * kv) * 8 : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+  }
+  const int rows_per = (M + gridDim.x - 1) / gridDim.x;
+  const int m0 = blockIdx.x * rows_per, m1 = min(M, m0 + rows_per);
+  for (int m = m0; m < m1; ++m) {
+    const float* xr = x + (long long)m * ldx;
+    const float* gr = dy + (long long)m * lddy;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+      if (pn[p] >= 0) {
+        const float g = gr[pn[p]];
+        const float4 a = *reinterpret_cast<const float4*>(xr + pk[p]);
+        const float4 b = *reinterpret_cast<const float4*>(xr + pk[p] + 4);
+        acc[p][0] = fmaf(g, a.x, acc[p][0]); acc[p][1] = fmaf(g, a.y, acc[p][1]);
+        acc[p][2] = fmaf(g, a.z, acc[p][2]); acc[p][3] = fmaf(g, a.w, acc[p][3]);
+        acc[p][4] = fmaf(g, b.x, acc[p][4]); acc[p][5] = fmaf(g, b.y, acc[p][5]);
+        acc[p][6] = fmaf(g, b.z, acc[p][6]); acc[p][7] = fmaf(g, b.w, acc[p][7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    if (pn[p] >= 0) {
+      float* o = dw + (long long)pn[p] * lddw + pk[p];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(o + j, acc[p][j]);
+    }
+  }
+}
+
 }  // namespace mtvaf
 
 using namespace mtvaf;
@@ -203,6 +295,50 @@ extern "C" int mtvaf_skinny_linear_f32(const float* x, int64_t ldx, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N <= 16) skinny_linear_kernel<16><<<(int)blocks, 256, 0, st>>>(x, ldx, w, ldw, bias, M, N, K, out, ldo);
   else skinny_linear_kernel<48><<<(int)blocks, 256, 0, st>>>(x, ldx, w, ldw, bias, M, N, K, out, ldo);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_skinny_linear_dgrad(const float* dy, int64_t lddy, const float* w, int64_t ldw, int M, int N,
+                                         int K, float p_drop, uint64_t seed, void* dx, int64_t lddx, int dx_dtype,
+                                         void* stream) {
+  MTVAF_REQUIRE(dy && w && dx && M > 0 && N > 0 && K > 0, "skinny_linear_dgrad: bad argument");
+  MTVAF_REQUIRE(N <= 16, "skinny_linear_dgrad: N=%d > 16 (use mtvaf_gemm_f32)", N);
+  MTVAF_REQUIRE(K % 4 == 0 && ldw % 4 == 0 && lddx % 4 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(dx) % 16 == 0,
+                "skinny_linear_dgrad: K / leading dims must be multiples of 4 and w, dx 16-byte aligned");
+  MTVAF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "skinny_linear_dgrad: bad dropout p");
+  uint32_t thr = 0;
+  float scale = 1.f;
+  if (p_drop > 0.f) {
+    const double t = (double)p_drop * 4294967296.0;
+    thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    scale = 1.f / (1.f - p_drop);
+  }
+  long long blocks = ((long long)M + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx_dtype == MTVAF_BF16)
+    skinny_dgrad_kernel<__nv_bfloat16, 16><<<(int)blocks, 256, 0, st>>>(dy, lddy, w, ldw, M, N, K, (__nv_bfloat16*)dx,
+                                                                        lddx, thr, scale, seed, step_source());
+  else
+    skinny_dgrad_kernel<float, 16><<<(int)blocks, 256, 0, st>>>(dy, lddy, w, ldw, M, N, K, (float*)dx, lddx, thr,
+                                                                scale, seed, step_source());
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mtvaf_skinny_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, int M, int N,
+                                         int K, float* dw, int64_t lddw, void* stream) {
+  MTVAF_REQUIRE(dy && x && dw && M > 0 && N > 0 && K > 0, "skinny_linear_wgrad: bad argument");
+  MTVAF_REQUIRE(K % 8 == 0 && ldx % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0,
+                "skinny_linear_wgrad: K %% 8 == 0, ldx %% 4 == 0 and x 16-byte aligned required");
+  MTVAF_REQUIRE((long long)N * (K / 8) <= 6 * 256, "skinny_linear_wgrad: N*K/8 = %lld > 1536 (use mtvaf_gemm_f32)",
+                (long long)N * (K / 8));
+  int blocks = sm_count();
+  if (blocks > M) blocks = M;
+  skinny_wgrad_kernel<6><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, M, N, K, dw, lddw);
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

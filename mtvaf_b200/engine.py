@@ -420,7 +420,12 @@ class Engine:
         # all 12 projectors in one skinny GEMM: [rows, 8H] x [n_layers*4, 8H]^T
         pw, pb = self._projector_pack()
         gs32 = ops.cast_f32(gs) if gs.dtype == BF16 else gs
-        gate_logits = ops.skinny_linear(gs32, pw, pb)            # [rows, 48], deterministic (no split-K atomics)
+        if cd == BF16:
+            # tensor cores, no split-K (deterministic): [rows, 8H] x [48, 8H]^T with fp32 logits out
+            pwb = torch.cat([f.wb("projectors.%d.weight" % l) for l in range(c.n_layers)], 0)
+            gate_logits = ops.gemm(gs, pwb, M=rows, N=4 * c.n_layers, K=W8, bias=pb, out_dtype=F32)
+        else:
+            gate_logits = ops.skinny_linear(gs32, pw, pb)        # [rows, 48], deterministic warp-per-row kernel
         kv, gates = ops.gate_fwd(guids, gate_logits, c.n_layers, n_img, B, H)
         saved.update(gs32=gs32, gate_logits=gate_logits, gates=gates)
         return kv, img_losses, (saved if save else None)
@@ -536,11 +541,16 @@ class Engine:
         ops.add_inplace(f.g("crf.end_transitions"), saved["d_e"])
         ops.add_inplace(f.g("crf.transitions"), saved["d_t"])
         de = d_em.view(T, n_tags)
-        ops.linear_wgrad(de, saved["seq_d"], f.g("fc.weight"))
         ops.colsum(de, f.g("fc.bias"))
-        dseq = ops.linear_dgrad(de, f.w("fc.weight"))                               # [T,H] fp32
-        if saved["p_d"] > 0:
-            dseq = ops.dropout_apply(dseq, saved["p_d"], saved["seed_d"])
+        if n_tags <= 16 and H % 8 == 0 and n_tags * (H // 8) <= 1536:
+            # skinny head: dedicated kernels; the data gradient comes out dropout-masked in the encoder's dtype
+            ops.skinny_linear_wgrad(de, saved["seq_d"], f.g("fc.weight"))
+            dseq = ops.skinny_linear_dgrad(de, f.w("fc.weight"), self.compute_dtype, saved["p_d"], saved["seed_d"])
+        else:
+            ops.linear_wgrad(de, saved["seq_d"], f.g("fc.weight"))
+            dseq = ops.linear_dgrad(de, f.w("fc.weight"))                           # [T,H] fp32
+            if saved["p_d"] > 0:
+                dseq = ops.dropout_apply(dseq, saved["p_d"], saved["seed_d"])
         grads[c.n_layers] = dseq
         if saved["use_probe"]:
             # loss += [prob_loss > 0.1] * prob_loss * beta * 2^-epoch  (probes/loss.py:14-16)
@@ -552,6 +562,6 @@ class Engine:
             dT = ops.rowscale(Tm, dn, 2.0 * saved["probe_coef"])
             ops.linear_wgrad(x7, dT, f.g("oneWordpsdProbe.oneWordpsdProbe.proj"))
             projc = self.cw("oneWordpsdProbe.oneWordpsdProbe.proj")
-            dx7 = ops.gemm(dT, projc, M=T, N=H, K=Tm.shape[1], out_dtype=F32)
+            dx7 = ops.gemm(dT, projc, M=T, N=H, K=Tm.shape[1], out_dtype=self.compute_dtype)
             grads[saved["probe_layer"]] = dx7
         return grads

@@ -37,6 +37,8 @@ SIGNATURES = {
     "mtvaf_set_gemm_impl": [_i],
     "mtvaf_gemm_f32": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
     "mtvaf_skinny_linear_f32": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp],
+    "mtvaf_skinny_linear_dgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _u64, _vp, _i64, _i, _vp],
+    "mtvaf_skinny_linear_wgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp],
     "mtvaf_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mtvaf_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "mtvaf_colsum": [_vp, _i64, _i, _i, _i, _vp, _vp],

@@ -153,6 +153,29 @@ def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+def skinny_linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out_dtype: torch.dtype, p_drop: float = 0.0,
+                        seed: int = 0) -> torch.Tensor:
+    """dx = dropout_mask(seed) * (dy w) / (1-p) for N = w.shape[0] <= 16, written in `out_dtype`."""
+    _cuda(dy, w)
+    assert dy.dtype == torch.float32 and w.dtype == torch.float32 and dy.stride(1) == 1 and w.stride(1) == 1
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
+    _check(_raw.mtvaf_skinny_linear_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), M, N, K, p_drop,
+                                          seed, dx.data_ptr(), dx.stride(0), dt(dx), _stream()), "skinny_linear_dgrad")
+    return dx
+
+
+def skinny_linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor):
+    """dw[N,K] += dy^T x (fp32) for skinny N."""
+    _cuda(dy, x, dw)
+    assert dy.dtype == torch.float32 and x.dtype == torch.float32 and dw.dtype == torch.float32
+    M, N = dy.shape
+    K = x.shape[1]
+    _check(_raw.mtvaf_skinny_linear_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K,
+                                          dw.data_ptr(), dw.stride(0), _stream()), "skinny_linear_wgrad")
+
+
 def skinny_splits(M: int, N: int, K: int) -> int:
     """split-K factor for the fp32 SIMT GEMM when the output has too few 128x128 tiles to fill the SMs."""
     tiles = ((M + 127) // 128) * ((N + 127) // 128)

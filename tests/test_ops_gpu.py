@@ -479,6 +479,23 @@ def test_skinny_linear(ops, M, N, K):
     assert rel_err(ops.skinny_linear(x, w), x.double() @ w.double().t()) < 1e-5
 
 
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(4099, 11, 768), (50, 16, 1024), (300, 3, 64)])
+def test_skinny_linear_backward(ops, out_dtype, M, N, K):
+    dy, w, x = rnd(M, N, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(M, K, seed=3)
+    dx = ops.skinny_linear_dgrad(dy, w, out_dtype)
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 1e-5
+    assert dx.dtype == out_dtype and rel_err(dx, dy.double() @ w.double()) < tol
+    # with the head's input dropout: same mask as dropout_apply on the [M, K] activation
+    dxd = ops.skinny_linear_dgrad(dy, w, out_dtype, 0.1, 4242)
+    keep = ops.dropout_apply(torch.ones(M, K, device=DEV), 0.1, 4242) > 0
+    want = torch.where(keep, (dy.double() @ w.double()) / 0.9, torch.zeros((), device=DEV, dtype=torch.float64))
+    assert rel_err(dxd, want) < tol
+    dw = torch.full((N, K), 0.25, device=DEV)
+    ops.skinny_linear_wgrad(dy, x, dw)
+    assert rel_err(dw, dy.double().t() @ x.double() + 0.25) < 1e-5
+
+
 def test_softmax_kl(ops):
     B, n, heads = 5, 2089, 4
     ld = 2096
