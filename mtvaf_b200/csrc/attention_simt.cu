@@ -482,7 +482,7 @@ using namespace mtvaf;
 static int g_attention_impl = 0;
 namespace mtvaf { int attention_impl_override() { return g_attention_impl; } }
 extern "C" int mtvaf_set_attention_impl(int impl) {
-  MTVAF_REQUIRE(impl == 0 || impl == 1, "attention impl must be 0 (auto) or 1 (SIMT)");
+  MTVAF_REQUIRE(impl >= 0 && impl <= 2, "attention impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05, generic backward)");
   g_attention_impl = impl;
   return 0;
 }
@@ -496,7 +496,7 @@ extern "C" int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* 
   dim3 grid((L + AQB - 1) / AQB, nh, B);
   cudaStream_t st = (cudaStream_t)stream;
   bool done = false;
-  if (dtype == MTVAF_BF16 && attention_impl_override() == 0 && ld_ctx % 8 == 0) {
+  if (dtype == MTVAF_BF16 && attention_impl_override() != 1 && ld_ctx % 8 == 0) {
     // tensor-core path (tcgen05): every shape of the benchmark configs; others fall through to SIMT
     AttnTcArgs ta;
     AttnTcMaps tm;
@@ -532,7 +532,7 @@ extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void
   cudaStream_t st = (cudaStream_t)stream;
   const int total = B * nh * L;
   dim3 gq((L + AQB - 1) / AQB, nh, B), gk((P + L + AQB - 1) / AQB, nh, B);
-  if (dtype == MTVAF_BF16 && attention_impl_override() == 0 && ld_ctx % 8 == 0 && ld_dctx % 8 == 0 &&
+  if (dtype == MTVAF_BF16 && attention_impl_override() != 1 && ld_ctx % 8 == 0 && ld_dctx % 8 == 0 &&
       ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(dctx) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0) {
     // tensor-core path (tcgen05): one CTA per (batch, head), L <= 128
@@ -540,6 +540,8 @@ extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void
     AttnTcMaps tm;
     bool ok = false;
     if (int rc = attn_tc_prepare(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, p_drop, seed, &ta, &tm, &ok)) return rc;
+    if (ok && attention_impl_override() == 0 && attn_bwd_pipe_supported(ta))
+      return attn_bwd_pipe_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st);
     if (ok && attn_bwd_tc_supported(ta))
       return attn_bwd_tc_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st);
   }

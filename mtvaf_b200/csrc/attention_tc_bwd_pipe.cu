@@ -1,0 +1,452 @@
+// Software-pipelined backward of the prefix ("fusion") self-attention for the reference shape of the path
+// (text length L <= 128, visual prefix P <= 16 rows: bert_model.py:538 forces P = 4 * (1 + 3) = 16).
+//
+// Same math as attention_tc_bwd.cu (flash-attention backward with the saved log-sum-exp,
+// models/modeling_roberta.py:218-278), but TWO (batch, head) items are in flight per SM: while the 16 SIMT warps
+// turn S / dP of item i into P / dS, the tensor core already holds the gradients of item i-1 (being drained) and
+// TMA is fetching item i+1.  What makes that possible is a different key layout and TMEM map:
+//   * keys are numbered TEXT rows first (one exact 128-key MMA tile), then the prefix rows (start of the next
+//     64-key chunk), so the text part of dK / dV is ONE 128 x 64 accumulator each, and the prefix part is
+//     computed TRANSPOSED, dK_p^T[d, key] = Q^T dS[:, prefix], as a 128 x 16 accumulator (A = Q / dO read as
+//     MN-major operands, B = the prefix columns of dS / P): 2 x 16 TMEM columns instead of 2 x 64, stored with
+//     d along the lanes = coalesced fp32 rows of dK_p / dV_p;
+//   * TMEM (512 columns): S [0,144) | dP [144,288) | dQ [288,352) | dK [352,416) | dV [416,480) |
+//     dK_p^T [480,496) | dV_p^T [496,512): the S / dP columns of item i+1 never alias the gradients of item i.
+// Warp roles (544 threads): warps 0..15 SIMT (thread = query row x quarter of the 8-key units), warp 16 lane 0 =
+// TMA + MMA issue.  Shared memory: Q, K, dO double-buffered, V single (free again once dP = dO V^T has retired),
+// P and dS single (free once the item's gradient MMAs have retired).  Everything is handed over through
+// mbarriers; the SIMT warps synchronise among themselves with a named barrier.
+#include "attention_tc.cuh"
+
+namespace mtvaf {
+using namespace ptx;
+
+namespace {
+
+constexpr int kSimtThreads = 512;
+constexpr int kPipeThreads = kSimtThreads + 32;
+constexpr float kLog2eP = 1.4426950408889634f;
+// TMEM columns
+constexpr int TC_S = 0, TC_DP = 144, TC_DQ = 288, TC_DK = 352, TC_DV = 416, TC_DKP = 480, TC_DVP = 496;
+
+struct PipeSmem {
+  int n_chunks, kv_rows;
+  size_t k_stride;
+  size_t off_ds, off_p, off_q, off_do, off_k, off_v, off_mask, off_exch, off_bar, total;
+};
+
+__host__ __device__ inline PipeSmem pipe_layout(int P8, int L64) {
+  PipeSmem s;
+  s.n_chunks = L64 / 64 + (P8 > 0 ? 1 : 0);
+  s.kv_rows = L64 + P8;                               // text rows then prefix rows, all covered by TMA boxes
+  s.k_stride = ((size_t)s.kv_rows * 128 + 1023) / 1024 * 1024;
+  size_t o = 0;
+  s.off_ds = o; o += (size_t)(s.n_chunks + 1) * 16384;   // +1: the 128-key text tile may read one chunk past
+  s.off_p = o;  o += (size_t)(s.n_chunks + 1) * 16384;
+  s.off_q = o;  o += 2 * 16384;
+  s.off_do = o; o += 2 * 16384;
+  s.off_k = o;  o += 2 * s.k_stride;
+  s.off_v = o;  o += s.k_stride;
+  s.off_mask = o; o += 2 * 256 * sizeof(float);
+  s.off_exch = o; o += 2 * 4 * 128 * sizeof(float);
+  s.off_bar = o; o += 128;
+  s.total = o + 1024;
+  return s;
+}
+
+__device__ __forceinline__ float pipe_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void simt_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                     const __grid_constant__ CUtensorMap tmKp, const __grid_constant__ CUtensorMap tmVp,
+                     const __grid_constant__ CUtensorMap tmdO, AttnTcArgs a, const float* __restrict__ lse,
+                     const __nv_bfloat16* __restrict__ ctx, long long ld_ctx, __nv_bfloat16* __restrict__ dqkv,
+                     long long ld_dqkv, float* __restrict__ dkp, float* __restrict__ dvp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const PipeSmem lay = pipe_layout(a.P8, a.L64);
+  uint8_t* sdS = smem + lay.off_ds;
+  uint8_t* sP = smem + lay.off_p;
+  uint8_t* sQ0 = smem + lay.off_q;
+  uint8_t* sdO0 = smem + lay.off_do;
+  uint8_t* sK0 = smem + lay.off_k;
+  uint8_t* sV = smem + lay.off_v;
+  float* sMask0 = reinterpret_cast<float*>(smem + lay.off_mask);          // [2][256] additive mask * log2(e)
+  float* sExch0 = reinterpret_cast<float*>(smem + lay.off_exch);          // [2][4][128] partial rowsum(dO o O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
+  uint64_t* bar_qk = bars;        // [2] Q + K tiles landed (TMA tx)
+  uint64_t* bar_do = bars + 2;    // [2] dO tile landed
+  uint64_t* bar_v = bars + 4;     //     V tile landed
+  uint64_t* bar_s = bars + 5;     //     S and dP in TMEM            (tcgen05.commit)
+  uint64_t* bar_p = bars + 6;     //     P and dS in smem, S/dP read (16 warp arrivals)
+  uint64_t* bar_g = bars + 7;     //     gradients in TMEM           (tcgen05.commit)
+  uint64_t* bar_o = bars + 8;     //     gradients drained           (16 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.nh * 64;
+  const int n_items = a.B * a.nh;
+  const int NT = a.L64;                                // first prefix key column / smem row
+  const int NS = (a.L64 + a.P8 + 15) / 16 * 16;        // MMA N of S / dP (<= 144)
+  const int cp = a.L64 / 64;                           // chunk that holds the prefix columns
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmKV); prefetch_tmap(&tmdO);
+    if (a.P8 > 0) { prefetch_tmap(&tmKp); prefetch_tmap(&tmVp); }
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_p, 16);
+    mbar_init(bar_g, 1);
+    mbar_init(bar_o, 16);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 16) tmem_alloc<512>(tmem_ptr);
+  // K / V rows [kv_rows, NS) are read by the MMAs but never loaded: zero them once (0 x garbage could be NaN)
+  for (int i = lay.kv_rows * 8 + tid; i < NS * 8; i += kPipeThreads) {
+    *reinterpret_cast<uint4*>(sK0 + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sK0 + lay.k_stride + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int first = blockIdx.x;
+
+  if (warp == 16) {
+    // ===================================== control: TMA + MMA issue ======================================
+    if (lane == 0) {
+      const uint32_t kv_bytes = (uint32_t)lay.kv_rows * 128u;
+      auto load_qkdo = [&](int item, int buf) {
+        const int b = item / a.nh, h = item - b * a.nh;
+        uint8_t* q = sQ0 + buf * 16384;
+        uint8_t* k = sK0 + buf * lay.k_stride;
+        mbar_arrive_expect_tx(&bar_qk[buf], 16384u + kv_bytes);
+        tma_load_2d(q, &tmQ, &bar_qk[buf], h * 64, b * a.L);
+        for (int r = 0; r < a.L64; r += 64) tma_load_2d(k + r * 128, &tmKV, &bar_qk[buf], H + h * 64, b * a.L + r);
+        for (int r = 0; r < a.P8; r += 8)
+          tma_load_2d(k + (NT + r) * 128, &tmKp, &bar_qk[buf], 0, (b * a.nh + h) * a.P + r);
+        mbar_arrive_expect_tx(&bar_do[buf], 16384u);
+        tma_load_2d(sdO0 + buf * 16384, &tmdO, &bar_do[buf], h * 64, b * a.L);
+      };
+      auto load_v = [&](int item) {
+        const int b = item / a.nh, h = item - b * a.nh;
+        mbar_arrive_expect_tx(bar_v, kv_bytes);
+        for (int r = 0; r < a.L64; r += 64) tma_load_2d(sV + r * 128, &tmKV, bar_v, 2 * H + h * 64, b * a.L + r);
+        for (int r = 0; r < a.P8; r += 8)
+          tma_load_2d(sV + (NT + r) * 128, &tmVp, bar_v, 0, (b * a.nh + h) * a.P + r);
+      };
+      if (first < n_items) { load_qkdo(first, 0); load_v(first); }
+      const uint32_t idesc_s = make_idesc_bf16(128, NS, false, false);
+      const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);
+      const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
+      const uint32_t idesc_p = make_idesc_bf16(128, a.P8 > 0 ? a.P8 : 16, true, true);
+      const uint32_t adS = smem_u32(sdS), aP = smem_u32(sP), aV = smem_u32(sV);
+      int il = 0;
+      for (int item = first; item < n_items; item += gridDim.x, ++il) {
+        const int buf = il & 1;
+        const uint32_t ph = il & 1, ph2 = (il >> 1) & 1;
+        const int next = item + gridDim.x;
+        const uint32_t aQ = smem_u32(sQ0 + buf * 16384), aK = smem_u32(sK0 + buf * lay.k_stride),
+                       adO = smem_u32(sdO0 + buf * 16384);
+        // ---- S = Q K^T, dP = dO V^T   (the S / dP columns are free: bar_p of the previous item was awaited
+        //      before that item's gradient MMAs were issued)
+        mbar_wait(&bar_qk[buf], ph2);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + TC_S, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        mbar_wait(&bar_do[buf], ph2);
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + TC_DP, make_smem_desc_sw128(adO + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        // ---- the other Q / K / dO buffers were last read by the previous item's gradient MMAs
+        if (il > 0) mbar_wait(bar_g, ph ^ 1);
+        if (next < n_items) load_qkdo(next, buf ^ 1);
+        mbar_wait(bar_s, ph);                           // dP retired: V is free
+        if (next < n_items) load_v(next);
+        // ---- gradients: need P / dS of this item and the previous item's gradients drained from TMEM
+        mbar_wait(bar_p, ph);
+        if (il > 0) mbar_wait(bar_o, ph ^ 1);
+        tc_fence_after();
+        {
+          // dQ[q, d] = sum_key dS[q, key] K[key, d]
+          const int ksteps = NS / 16;
+          for (int j = 0; j < ksteps; ++j)
+            umma_f16_ss(tmem_base + TC_DQ, make_smem_desc_sw128(adS + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
+                        make_smem_desc_sw128(aK + j * 2048, 8192, 1024), idesc_q, j > 0 ? 1u : 0u);
+          // text keys: dK[key, d] = sum_q dS[q, key] Q[q, d] ; dV[key, d] = sum_q P[q, key] dO[q, d]
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_f16_ss(tmem_base + TC_DK, make_smem_desc_sw128(adS + j * 2048, 16384, 1024),
+                        make_smem_desc_sw128(aQ + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1u : 0u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_f16_ss(tmem_base + TC_DV, make_smem_desc_sw128(aP + j * 2048, 16384, 1024),
+                        make_smem_desc_sw128(adO + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1u : 0u);
+          if (a.P8 > 0) {
+            // prefix keys, transposed: dK_p^T[d, key] = sum_q Q[q, d] dS[q, key] ; dV_p^T[d, key] = sum_q dO[q, d] P[q, key]
+            // (A = Q / dO as MN-major operands: rows 64..127 of the M = 128 tile read the second half of the
+            //  tile's own bytes, finite values whose output lanes are never stored)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              umma_f16_ss(tmem_base + TC_DKP, make_smem_desc_sw128(aQ + j * 2048, 8192, 1024),
+                          make_smem_desc_sw128(adS + cp * 16384 + j * 2048, 16384, 1024), idesc_p, j > 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              umma_f16_ss(tmem_base + TC_DVP, make_smem_desc_sw128(adO + j * 2048, 8192, 1024),
+                          make_smem_desc_sw128(aP + cp * 16384 + j * 2048, 16384, 1024), idesc_p, j > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_g);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================ SIMT warps ==============================================
+    const int quad = warp & 3, part = warp >> 2;       // TMEM lane group / quarter of the columns
+    const int row = quad * 32 + lane;                  // query row == TMEM lane
+    const bool row_ok = row < a.L;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float sc2 = a.scale * kLog2eP;
+    const int row8 = row & 7;
+    const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
+    const int units = NS >> 3;
+    const int dcol = part * 16;
+    const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
+    const float ds_coef = a.scale / a.drop_scale;      // dS = P' * (scale / drop_scale) * (dP' - D)
+
+    // smem key `k`: text row k (k < L64), prefix row k - NT (k >= NT)
+    auto fetch_mask = [&](int item) -> float {
+      if (tid >= NS) return 0.f;
+      const int b = item / a.nh;
+      if (tid < NT) return (tid < a.L) ? (a.key_mask[(long long)b * a.L + tid] != 0 ? 0.f : -10000.0f * kLog2eP) : -INFINITY;
+      return (tid - NT < a.P) ? 0.f : -INFINITY;
+    };
+    auto fetch_lse = [&](int item) -> float {
+      const int b = item / a.nh, h = item - b * a.nh;
+      return row_ok ? lse[((long long)b * a.nh + h) * a.L + row] * kLog2eP - log2_ds : INFINITY;
+    };
+    auto fetch_o = [&](int item, uint4& o0, uint4& o1) {
+      o0 = make_uint4(0, 0, 0, 0);
+      o1 = o0;
+      if (row_ok) {
+        const int b = item / a.nh, h = item - b * a.nh;
+        const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)b * a.L + row) * ld_ctx + h * 64 + dcol);
+        o0 = po[0];
+        o1 = po[1];
+      }
+    };
+    // drain the gradients of `item` from TMEM (bar_g of that item has been awaited by the caller)
+    auto store_item = [&](int item) {
+      const int b = item / a.nh, h = item - b * a.nh;
+      uint32_t r[16];
+      // dQ
+      tmem_ld_32x32b_x16(t_row + TC_DQ + dcol, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint4* o = reinterpret_cast<uint4*>(dqkv + ((long long)b * a.L + row) * ld_dqkv + h * 64 + dcol);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+          w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+          w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+          w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+          o[v] = w;
+        }
+      }
+      // dK, dV of the text keys: lane = key row
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        __syncwarp();
+        tmem_ld_32x32b_x16(t_row + (which ? TC_DV : TC_DK) + dcol, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint4* o = reinterpret_cast<uint4*>(dqkv + ((long long)b * a.L + row) * ld_dqkv + (which + 1) * H + h * 64 +
+                                              dcol);
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+            w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+            w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+            w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+            o[v] = w;
+          }
+        }
+      }
+      // prefix rows, transposed accumulators: lane = head-dim index d (lanes 0..63), column = prefix key
+      if (a.P8 > 0 && part < 2 && quad < 2) {            // warp-uniform
+        float* dst = part ? dvp : dkp;
+        __syncwarp();
+        tmem_ld_32x32b_x16(t_row + (part ? TC_DVP : TC_DKP), r);
+        tmem_ld_wait();
+        if (dst) {
+          float* o = dst + ((long long)b * a.nh + h) * a.P * 64 + row;      // row == d here
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < a.P) o[j * 64] = __uint_as_float(r[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_o);
+    };
+
+    float m_next = 0.f, lse_next = 0.f;
+    uint4 o0n = make_uint4(0, 0, 0, 0), o1n = o0n;
+    if (first < n_items) {
+      m_next = fetch_mask(first);
+      lse_next = fetch_lse(first);
+      fetch_o(first, o0n, o1n);
+    }
+    int il = 0;
+    int prev = -1;
+    for (int item = first; item < n_items; item += gridDim.x, ++il) {
+      const int b = item / a.nh, h = item - b * a.nh;
+      const int buf = il & 1;
+      const uint32_t ph = il & 1, ph2 = (il >> 1) & 1;
+      const int next = item + gridDim.x;
+      float* sMask = sMask0 + buf * 256;
+      float* sExch = sExch0 + buf * 512;
+      const uint8_t* sdO = sdO0 + buf * 16384;
+      // ---- this item's prefetched scalars; D_q = rowsum(dO o O) over this thread's 16 columns
+      if (tid < NS) sMask[tid] = m_next;
+      const float lse2 = lse_next;
+      const uint4 o0 = o0n, o1 = o1n;
+      mbar_wait(&bar_do[buf], ph2);
+      {
+        const uint8_t* pd = sdO + prow_off;
+        const uint4 d0 = *reinterpret_cast<const uint4*>(pd + (((part * 2) ^ row8) << 4));
+        const uint4 d1 = *reinterpret_cast<const uint4*>(pd + (((part * 2 + 1) ^ row8) << 4));
+        float acc = 0.f;
+        const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 x = unpack_bf16x2(dw[j]), y = unpack_bf16x2(ow[j]);
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+        }
+        sExch[part * 128 + row] = acc;
+      }
+      // the next item's scalars travel while this item is processed
+      if (next < n_items) {
+        m_next = fetch_mask(next);
+        lse_next = fetch_lse(next);
+        fetch_o(next, o0n, o1n);
+      }
+      // ---- drain the previous item's gradients (its MMAs were issued one softmax ago); this also guarantees
+      //      that P / dS in shared memory are free again
+      if (prev >= 0) {
+        mbar_wait(bar_g, ph ^ 1);
+        tc_fence_after();
+        store_item(prev);
+      }
+      simt_barrier();                                    // publishes sMask and sExch
+      const float dsum = (sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row]);
+      const uint32_t rowkey =
+          a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
+
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      // ---- P and dS for this thread's (row, every 4th 8-key unit).  P' = P / (1-p) is born scaled (the dropout
+      // scale rides in the exponent: lse2 carries -log2(scale)); dropped keys are zeroed in P' and in dP.
+      for (int u = part; u < units; u += 4) {
+        const int c = u << 3;
+        uint32_t rs[8], rd[8];
+        tmem_ld_32x32b_x8(t_row + TC_S + c, rs);
+        tmem_ld_32x32b_x8(t_row + TC_DP + c, rd);
+        const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
+        const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
+        const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        tmem_ld_wait();
+        float p[8], dp[8], ds[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // masked / absent keys and rows past L give exp2(-inf) = 0 (S and dP are finite: padded K/V rows are 0)
+          p[j] = pipe_ex2(fmaf(__uint_as_float(rs[j]), sc2, mk[j] - lse2));
+          dp[j] = __uint_as_float(rd[j]) * a.drop_scale;
+          ds[j] = p[j] * ds_coef;
+        }
+        // reference key numbering for the dropout hash: prefix rows 0..P-1, then the text rows
+        if (a.drop_thr) attn_drop_apply8(rowkey, c < NT ? a.P + c : c - NT, a.drop_thr, p, dp);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ds[j] *= dp[j] - dsum;
+        const uint32_t off = (u >> 3) * 16384 + prow_off + (((u & 7) ^ row8) << 4);
+        uint4 w;
+        w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
+        w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(sP + off) = w;
+        w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
+        w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
+        *reinterpret_cast<uint4*>(sdS + off) = w;
+      }
+      // columns [NS, 64 * n_chunks) of the prefix chunk feed accumulator rows / columns that are never stored
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      prev = item;
+    }
+    if (prev >= 0) {
+      mbar_wait(bar_g, (il - 1) & 1);
+      tc_fence_after();
+      store_item(prev);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+bool attn_bwd_pipe_supported(const AttnTcArgs& a) {
+  if (a.L > 128 || a.P8 > 16) return false;
+  return pipe_layout(a.P8, a.L64).total <= 227 * 1024;
+}
+
+int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
+                         int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
+                         cudaStream_t st) {
+  MTVAF_REQUIRE(ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0,
+                "attention_bwd(pipe): dqkv must be 16-byte aligned with ld %% 8 == 0");
+  MTVAF_REQUIRE(ld_ctx % 8 == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
+                "attention_bwd(pipe): ctx must be 16-byte aligned with ld %% 8 == 0");
+  CUtensorMap tmdO;
+  const uint64_t T = (uint64_t)a.B * a.L;
+  const uint64_t H = (uint64_t)a.nh * 64;
+  int rc = make_tmap_bf16_2d(&tmdO, dctx, H, T, ld_dctx, 64, 128);
+  if (rc) return rc;
+  const PipeSmem lay = pipe_layout(a.P8, a.L64);
+  static bool set = false;
+  if (!set) {
+    MTVAF_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    set = true;
+  }
+  const int n_items = a.B * a.nh;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  attn_bwd_pipe_kernel<<<grid, kPipeThreads, lay.total, st>>>(m.q, m.kv, m.kp, m.vp, tmdO, a, lse,
+                                                             (const __nv_bfloat16*)ctx, ld_ctx, (__nv_bfloat16*)dqkv,
+                                                             ld_dqkv, dkp, dvp);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mtvaf

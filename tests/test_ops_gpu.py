@@ -368,7 +368,7 @@ def test_attention_dropout_keep_rate(ops, dtype):
 
 @pytest.mark.parametrize("B,Lq,P,p_drop", [(2, 128, 16, 0.1), (3, 40, 36, 0.1), (2, 100, 5, 0.0), (4, 128, 64, 0.1),
                                             (2, 128, 0, 0.1), (1, 17, 4, 0.0), (2, 64, 5, 0.1), (32, 128, 16, 0.1),
-                                            (13, 96, 36, 0.0)])
+                                            (13, 96, 36, 0.0), (14, 50, 16, 0.1), (30, 128, 9, 0.0)])
 def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
     """The tcgen05 forward/backward kernels and the SIMT kernels share one dropout hash: on bf16 inputs they
     must agree to bf16 rounding, with and without probability dropout, including ragged key masks."""
@@ -383,7 +383,7 @@ def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
     dctx = rnd(B * Lq, nh * d, seed=14, dtype=bf)
     res = {}
     try:
-        for impl in ("simt", "auto"):
+        for impl in ("simt", "tc_generic", "auto"):
             ops.set_attention_impl(impl)
             ctx, lse, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p_drop, seed=99)
             dkp = torch.zeros(B, nh, P, d, device=DEV) if P else None
@@ -393,11 +393,12 @@ def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
     finally:
         ops.set_attention_impl("auto")
     names = ("ctx", "lse", "dqkv", "dkp", "dvp")
-    for nm, a, b in zip(names, res["auto"], res["simt"]):
-        if a is None:
-            continue
-        assert torch.isfinite(a.float()).all(), nm
-        assert rel_err(a, b) < 2e-2, nm
+    for impl in ("tc_generic", "auto"):          # auto = software-pipelined backward when L <= 128 and P <= 16
+        for nm, a, b in zip(names, res[impl], res["simt"]):
+            if a is None:
+                continue
+            assert torch.isfinite(a.float()).all(), (impl, nm)
+            assert rel_err(a, b) < 2e-2, (impl, nm)
 
 
 # ---------------------------------------------------------------------------------------- fusion
