@@ -41,8 +41,12 @@ __host__ __device__ inline PipeSmem pipe_layout(int P8, int L64) {
   s.kv_rows = L64 + P8;                               // text rows then prefix rows, all covered by TMA boxes
   s.k_stride = ((size_t)s.kv_rows * 128 + 1023) / 1024 * 1024;
   size_t o = 0;
-  s.off_ds = o; o += (size_t)(s.n_chunks + 1) * 16384;   // +1: the 128-key text tile may read one chunk past
-  s.off_p = o;  o += (size_t)(s.n_chunks + 1) * 16384;
+  // chunks: text keys (L64 / 64 chunks) then one prefix chunk.  The 128-key text tile of dK / dV reads chunks
+  // 0 and 1; with L64 == 64 chunk 1 is the prefix chunk (rows of the accumulator that are never stored) and with
+  // no prefix at all a second (never written) chunk is reserved for it
+  const int alloc_chunks = s.n_chunks < 2 ? 2 : s.n_chunks;
+  s.off_ds = o; o += (size_t)alloc_chunks * 16384;
+  s.off_p = o;  o += (size_t)alloc_chunks * 16384;
   s.off_q = o;  o += 2 * 16384;
   s.off_do = o; o += 2 * 16384;
   s.off_k = o;  o += 2 * s.k_stride;
@@ -146,7 +150,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t idesc_s = make_idesc_bf16(128, NS, false, false);
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);
       const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
-      const uint32_t idesc_p = make_idesc_bf16(128, a.P8 > 0 ? a.P8 : 16, true, true);
+      const uint32_t idesc_p = make_idesc_bf16(128, 16, true, true);     // N = 16 >= P8 (UMMA: N % 16 == 0)
       const uint32_t adS = smem_u32(sdS), aP = smem_u32(sP), aV = smem_u32(sV);
       int il = 0;
       for (int item = first; item < n_items; item += gridDim.x, ++il) {
