@@ -39,7 +39,8 @@ __host__ __device__ inline PipeSmem pipe_layout(int P8, int L64) {
   PipeSmem s;
   s.n_chunks = L64 / 64 + (P8 > 0 ? 1 : 0);
   s.kv_rows = L64 + P8;                               // text rows then prefix rows, all covered by TMA boxes
-  s.k_stride = ((size_t)s.kv_rows * 128 + 1023) / 1024 * 1024;
+  const int ns = (L64 + P8 + 15) / 16 * 16;            // rows the MMAs read (>= kv_rows; the excess is zero-filled)
+  s.k_stride = ((size_t)(ns > s.kv_rows ? ns : s.kv_rows) * 128 + 1023) / 1024 * 1024;
   size_t o = 0;
   // chunks: text keys (L64 / 64 chunks) then one prefix chunk.  The 128-key text tile of dK / dV reads chunks
   // 0 and 1; with L64 == 64 chunk 1 is the prefix chunk (rows of the accumulator that are never stored) and with
@@ -151,29 +152,42 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);
       const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
       const uint32_t idesc_p = make_idesc_bf16(128, 16, true, true);     // N = 16 >= P8 (UMMA: N % 16 == 0)
-      const uint32_t adS = smem_u32(sdS), aP = smem_u32(sP), aV = smem_u32(sV);
+      // The issuing thread is on the critical path of every item, so its instruction stream is kept short: the
+      // descriptors of each operand are built once (per buffer) and only advanced -- the start-address field holds
+      // addr >> 4, hence desc(base + off) = desc(base) + (off >> 4).
+      // buffer 1 lives at a fixed byte distance from buffer 0: same trick for the per-buffer descriptors
+      const uint64_t q_k0 = make_smem_desc_sw128(smem_u32(sQ0), 16, 1024);
+      const uint64_t k_k0 = make_smem_desc_sw128(smem_u32(sK0), 16, 1024);
+      const uint64_t o_k0 = make_smem_desc_sw128(smem_u32(sdO0), 16, 1024);
+      const uint64_t k_mn0 = make_smem_desc_sw128(smem_u32(sK0), 8192, 1024);
+      const uint64_t q_mn0 = make_smem_desc_sw128(smem_u32(sQ0), 8192, 1024);
+      const uint64_t o_mn0 = make_smem_desc_sw128(smem_u32(sdO0), 8192, 1024);
+      const uint64_t q_step = 16384 >> 4, k_step = lay.k_stride >> 4;
+      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      const uint64_t dS_k = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
+      const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), 16384, 1024);
+      const uint64_t P_mn = make_smem_desc_sw128(smem_u32(sP), 16384, 1024);
+      const int ksteps = NS / 16;
       int il = 0;
       for (int item = first; item < n_items; item += gridDim.x, ++il) {
         const int buf = il & 1;
         const uint32_t ph = il & 1, ph2 = (il >> 1) & 1;
         const int next = item + gridDim.x;
-        const uint32_t aQ = smem_u32(sQ0 + buf * 16384), aK = smem_u32(sK0 + buf * lay.k_stride),
-                       adO = smem_u32(sdO0 + buf * 16384);
+        const uint64_t q_k = q_k0 + buf * q_step, k_k = k_k0 + buf * k_step, o_k = o_k0 + buf * q_step;
+        const uint64_t k_mn = k_mn0 + buf * k_step, q_mn = q_mn0 + buf * q_step, o_mn = o_mn0 + buf * q_step;
         // ---- S = Q K^T, dP = dO V^T   (the S / dP columns are free: bar_p of the previous item was awaited
         //      before that item's gradient MMAs were issued)
         mbar_wait(&bar_qk[buf], ph2);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + TC_S, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
-                      make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + TC_S, q_k + k * 2, k_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
         mbar_wait(&bar_do[buf], ph2);
         mbar_wait(bar_v, ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + TC_DP, make_smem_desc_sw128(adO + k * 32, 16, 1024),
-                      make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + TC_DP, o_k + k * 2, dV_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(bar_s);
         // ---- the other Q / K / dO buffers were last read by the previous item's gradient MMAs
         if (il > 0) mbar_wait(bar_g, ph ^ 1);
@@ -184,34 +198,31 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(bar_p, ph);
         if (il > 0) mbar_wait(bar_o, ph ^ 1);
         tc_fence_after();
-        {
-          // dQ[q, d] = sum_key dS[q, key] K[key, d]
-          const int ksteps = NS / 16;
-          for (int j = 0; j < ksteps; ++j)
-            umma_f16_ss(tmem_base + TC_DQ, make_smem_desc_sw128(adS + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                        make_smem_desc_sw128(aK + j * 2048, 8192, 1024), idesc_q, j > 0 ? 1u : 0u);
-          // text keys: dK[key, d] = sum_q dS[q, key] Q[q, d] ; dV[key, d] = sum_q P[q, key] dO[q, d]
+        // dQ[q, d] = sum_key dS[q, key] K[key, d]   (K-major dS: 64-key chunks of 16 KB, 32 B per 16-key step)
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          if (j < ksteps)
+            umma_f16_ss(tmem_base + TC_DQ, dS_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + j * 128, idesc_q,
+                        j > 0 ? 1u : 0u);
+        // text keys: dK[key, d] = sum_q dS[q, key] Q[q, d] ; dV[key, d] = sum_q P[q, key] dO[q, d]
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_f16_ss(tmem_base + TC_DK, dS_mn + j * 128, q_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_f16_ss(tmem_base + TC_DV, P_mn + j * 128, o_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
+        if (a.P8 > 0) {
+          // prefix keys, transposed: dK_p^T[d, key] = sum_q Q[q, d] dS[q, key] ; dV_p^T[d, key] = sum_q dO[q, d] P[q, key]
+          // (A = Q / dO as MN-major operands: rows 64..127 of the M = 128 tile read past the 64 real columns,
+          //  finite or not: their output lanes are never stored)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            umma_f16_ss(tmem_base + TC_DK, make_smem_desc_sw128(adS + j * 2048, 16384, 1024),
-                        make_smem_desc_sw128(aQ + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1u : 0u);
+            umma_f16_ss(tmem_base + TC_DKP, q_mn + j * 128, dS_mn + cp * 1024 + j * 128, idesc_p,
+                        j > 0 ? 1u : 0u);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            umma_f16_ss(tmem_base + TC_DV, make_smem_desc_sw128(aP + j * 2048, 16384, 1024),
-                        make_smem_desc_sw128(adO + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1u : 0u);
-          if (a.P8 > 0) {
-            // prefix keys, transposed: dK_p^T[d, key] = sum_q Q[q, d] dS[q, key] ; dV_p^T[d, key] = sum_q dO[q, d] P[q, key]
-            // (A = Q / dO as MN-major operands: rows 64..127 of the M = 128 tile read the second half of the
-            //  tile's own bytes, finite values whose output lanes are never stored)
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              umma_f16_ss(tmem_base + TC_DKP, make_smem_desc_sw128(aQ + j * 2048, 8192, 1024),
-                          make_smem_desc_sw128(adS + cp * 16384 + j * 2048, 16384, 1024), idesc_p, j > 0 ? 1u : 0u);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              umma_f16_ss(tmem_base + TC_DVP, make_smem_desc_sw128(adO + j * 2048, 8192, 1024),
-                          make_smem_desc_sw128(aP + cp * 16384 + j * 2048, 16384, 1024), idesc_p, j > 0 ? 1u : 0u);
-          }
+            umma_f16_ss(tmem_base + TC_DVP, o_mn + j * 128, P_mn + cp * 1024 + j * 128, idesc_p,
+                        j > 0 ? 1u : 0u);
         }
         umma_commit(bar_g);
       }
