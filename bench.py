@@ -165,6 +165,9 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The gradient all-reduce has the whole backward pass to hide behind (500 MB per ~15 ms): a few CTAs are
+        # plenty, and every SM NCCL does not occupy stays with the persistent tcgen05 kernels (one CTA per SM).
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
 
     from oracle.make_golden import hf_config          # config helper only (no oracle arithmetic)
@@ -352,7 +355,16 @@ def main():
                                               "CPU eager; no optimizer step)" % args.cpu_sample_batch}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # tear down in dependency order: the captured graph holds NCCL kernels of this communicator
+        if graphed is not None:
+            graphed.close()
+            graphed = None
+        barrier()
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))   # never let a teardown hang outlive the result
+        watchdog.daemon = True
+        watchdog.start()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

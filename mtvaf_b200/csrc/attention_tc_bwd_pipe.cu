@@ -379,15 +379,12 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       // ---- P and dS for this thread's (row, every 4th 8-key unit).  P' = P / (1-p) is born scaled (the dropout
       // scale rides in the exponent: lse2 carries -log2(scale)); dropped keys are zeroed in P' and in dP.
-      for (int u = part; u < units; u += 4) {
+      // The TMEM loads of the NEXT unit are in flight while the current one is processed (ping-pong registers).
+      auto process_unit = [&](int u, const uint32_t (&rs)[8], const uint32_t (&rd)[8]) {
         const int c = u << 3;
-        uint32_t rs[8], rd[8];
-        tmem_ld_32x32b_x8(t_row + TC_S + c, rs);
-        tmem_ld_32x32b_x8(t_row + TC_DP + c, rd);
         const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
         const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
         const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        tmem_ld_wait();
         float p[8], dp[8], ds[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -408,6 +405,30 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
         w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
         *reinterpret_cast<uint4*>(sdS + off) = w;
+      };
+      {
+        uint32_t sa[8], da[8], sb[8], db[8];
+        int u = part;
+        if (u < units) {
+          tmem_ld_32x32b_x8(t_row + TC_S + (u << 3), sa);
+          tmem_ld_32x32b_x8(t_row + TC_DP + (u << 3), da);
+        }
+        for (; u < units; u += 8) {
+          tmem_ld_wait();
+          if (u + 4 < units) {
+            tmem_ld_32x32b_x8(t_row + TC_S + ((u + 4) << 3), sb);
+            tmem_ld_32x32b_x8(t_row + TC_DP + ((u + 4) << 3), db);
+          }
+          process_unit(u, sa, da);
+          if (u + 4 < units) {
+            tmem_ld_wait();
+            if (u + 8 < units) {
+              tmem_ld_32x32b_x8(t_row + TC_S + ((u + 8) << 3), sa);
+              tmem_ld_32x32b_x8(t_row + TC_DP + ((u + 8) << 3), da);
+            }
+            process_unit(u + 4, sb, db);
+          }
+        }
       }
       // columns [NS, 64 * n_chunks) of the prefix chunk feed accumulator rows / columns that are never stored
       fence_proxy_async_smem();

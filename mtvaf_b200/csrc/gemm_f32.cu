@@ -223,7 +223,33 @@ skinny_wgrad_kernel(const float* __restrict__ dy, long long lddy, const float* _
   }
   const int rows_per = (M + gridDim.x - 1) / gridDim.x;
   const int m0 = blockIdx.x * rows_per, m1 = min(M, m0 + rows_per);
-  for (int m = m0; m < m1; ++m) {
+  // two rows per iteration: twice the loads in flight per thread (the loop is latency-bound, not bandwidth-bound)
+  int m = m0;
+  for (; m + 1 < m1; m += 2) {
+    const float* xr0 = x + (long long)m * ldx;
+    const float* xr1 = xr0 + ldx;
+    const float* gr0 = dy + (long long)m * lddy;
+    const float* gr1 = gr0 + lddy;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+      if (pn[p] >= 0) {
+        const float g0 = gr0[pn[p]], g1 = gr1[pn[p]];
+        const float4 a0 = *reinterpret_cast<const float4*>(xr0 + pk[p]);
+        const float4 b0 = *reinterpret_cast<const float4*>(xr0 + pk[p] + 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(xr1 + pk[p]);
+        const float4 b1 = *reinterpret_cast<const float4*>(xr1 + pk[p] + 4);
+        acc[p][0] = fmaf(g0, a0.x, acc[p][0]); acc[p][1] = fmaf(g0, a0.y, acc[p][1]);
+        acc[p][2] = fmaf(g0, a0.z, acc[p][2]); acc[p][3] = fmaf(g0, a0.w, acc[p][3]);
+        acc[p][4] = fmaf(g0, b0.x, acc[p][4]); acc[p][5] = fmaf(g0, b0.y, acc[p][5]);
+        acc[p][6] = fmaf(g0, b0.z, acc[p][6]); acc[p][7] = fmaf(g0, b0.w, acc[p][7]);
+        acc[p][0] = fmaf(g1, a1.x, acc[p][0]); acc[p][1] = fmaf(g1, a1.y, acc[p][1]);
+        acc[p][2] = fmaf(g1, a1.z, acc[p][2]); acc[p][3] = fmaf(g1, a1.w, acc[p][3]);
+        acc[p][4] = fmaf(g1, b1.x, acc[p][4]); acc[p][5] = fmaf(g1, b1.y, acc[p][5]);
+        acc[p][6] = fmaf(g1, b1.z, acc[p][6]); acc[p][7] = fmaf(g1, b1.w, acc[p][7]);
+      }
+    }
+  }
+  for (; m < m1; ++m) {
     const float* xr = x + (long long)m * ldx;
     const float* gr = dy + (long long)m * lddy;
 #pragma unroll
@@ -336,8 +362,9 @@ extern "C" int mtvaf_skinny_linear_wgrad(const float* dy, int64_t lddy, const fl
                 "skinny_linear_wgrad: K %% 8 == 0, ldx %% 4 == 0 and x 16-byte aligned required");
   MTVAF_REQUIRE((long long)N * (K / 8) <= 6 * 256, "skinny_linear_wgrad: N*K/8 = %lld > 1536 (use mtvaf_gemm_f32)",
                 (long long)N * (K / 8));
-  int blocks = sm_count();
-  if (blocks > M) blocks = M;
+  int blocks = sm_count() * 4;                  // 4 resident blocks per SM hide the load latency of the row walk
+  if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
+  if (blocks < 1) blocks = 1;
   skinny_wgrad_kernel<6><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, M, N, K, dw, lddw);
   MTVAF_LAUNCH_CHECK();
   return 0;

@@ -97,4 +97,9 @@ class GraphedTrainStep:
         return self.loss
 
     def close(self):
+        """Release the captured graph (and the NCCL kernels it references) and unregister the step counter."""
         ops.set_step_source(None)
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph.reset()
+            self.graph = None

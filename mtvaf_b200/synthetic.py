@@ -78,7 +78,8 @@ def encoder_param_shapes(cfg, prefix="bert.") -> "OrderedDict[str, tuple]":
 
 
 def init_params(cfg, *, seed: int = 1234, with_fusion: bool = True, n_aux: int = 3, n_anp: int = 2089,
-                num_labels: int = 11, probe_rank: int = None, ln_jitter: float = 0.0) -> "OrderedDict[str, torch.Tensor]":
+                num_labels: int = 11, probe_rank: int = None, ln_jitter: float = 0.0,
+                with_span: bool = False) -> "OrderedDict[str, torch.Tensor]":
     """Random-init parameter dict keyed like the reference state_dict.
 
     Encoder: the reference's `_init_weights` (models/modeling_roberta.py:695-709): Linear/Embedding
@@ -118,4 +119,39 @@ def init_params(cfg, *, seed: int = 1234, with_fusion: bool = True, n_aux: int =
     p["fc.bias"] = torch.randn(num_labels, generator=g) * 0.02
     r = probe_rank if probe_rank is not None else H // 2
     p["oneWordpsdProbe.oneWordpsdProbe.proj"] = torch.rand(H, r, generator=g) * 0.1 - 0.05   # probes/probe.py:60
+    if with_span:
+        # heads of the span variant TVNetSAModel (models/bert_model.py:205-212)
+        g2 = torch.Generator().manual_seed(seed + 7919)
+        for name, out_f in (("dense", H), ("unary_affine", 1), ("binary_affine", 2), ("classifier", 4)):
+            p[name + ".weight"] = torch.randn(out_f, H, generator=g2) * (1.0 / H) ** 0.5
+            p[name + ".bias"] = torch.randn(out_f, generator=g2) * 0.02
     return p
+
+
+def make_span_batch(B: int, L: int, *, M: int = 20, vocab: int = 50265, shape: str = "twitter2015", n_aux: int = 3,
+                    seed: int = 2024, with_images: bool = True) -> Dict[str, torch.Tensor]:
+    """Synthetic batch of the span variant (TVNetSAModel.forward, models/bert_model.py:246-252): multi-hot
+    start/end positions, up to M candidate spans per sentence (padded with the (0, 0) span, label mask 0),
+    4-way polarity labels."""
+    b = make_batch(B, L, vocab=vocab, shape=shape, n_aux=n_aux, seed=seed, with_images=with_images)
+    b.pop("labels")
+    b.pop("imagelabel", None)
+    g = torch.Generator().manual_seed(seed + 31337)
+    lens = b["attention_mask"].sum(1)
+    starts = torch.zeros(B, M, dtype=torch.long)
+    ends = torch.zeros(B, M, dtype=torch.long)
+    lmask = torch.zeros(B, M, dtype=torch.long)
+    sp = torch.zeros(B, L, dtype=torch.long)
+    ep = torch.zeros(B, L, dtype=torch.long)
+    for i in range(B):
+        n = int(torch.randint(1, min(M, 6) + 1, (1,), generator=g))
+        for j in range(n):
+            s0 = int(torch.randint(1, max(2, int(lens[i]) - 1), (1,), generator=g))
+            w = int(torch.randint(0, 4, (1,), generator=g))
+            e0 = min(s0 + w, int(lens[i]) - 1)
+            starts[i, j], ends[i, j], lmask[i, j] = s0, e0, 1
+            sp[i, s0] = 1
+            ep[i, e0] = 1
+    b.update(start_positions=sp, end_positions=ep, span_starts=starts, span_ends=ends,
+             polarity_labels=torch.randint(0, 4, (B, M), generator=g) * lmask, label_masks=lmask)
+    return b

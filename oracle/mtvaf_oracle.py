@@ -385,3 +385,86 @@ def tvnet2_forward(p, cfg: EncoderCfg, batch: Dict[str, Tensor], *, use_prefix=T
         out["loss"] = nll + img_term                                              # :530
     out["img_loss"] = img_term
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# span variant: TVNetSAModel.forward / extraction / classification (models/bert_model.py:246-376)
+# --------------------------------------------------------------------------------------------
+def span_representation(span_starts: Tensor, span_ends: Tensor, x: Tensor, input_mask: Tensor):
+    """get_span_representation (models/bert_model.py:147-172): spans index the COMPACTED token stream (all
+    tokens with mask 1, sentence after sentence), clamped to its last element; JR = widest span."""
+    mask = input_mask.to(span_starts.dtype)
+    input_len = mask.sum(-1)
+    word_offset = torch.cumsum(input_len, 0) - input_len
+    s = (span_starts + word_offset.unsqueeze(1)).reshape(-1)
+    e = (span_ends + word_offset.unsqueeze(1)).reshape(-1)
+    width = e - s + 1
+    JR = int(width.max())
+    B, L, H = x.shape
+    flat = x.reshape(B * L, H)[mask.reshape(-1).nonzero().squeeze(-1), :]        # flatten_emb_by_sentence :140-145
+    total = flat.shape[0]
+    idx = torch.arange(JR).unsqueeze(0) + s.unsqueeze(1)
+    idx = torch.minimum(idx, torch.full_like(idx, total - 1))                   # :165
+    span_emb = flat[idx, :]                                                      # [N*M, JR, H]
+    span_mask = torch.arange(JR).unsqueeze(0) < width.unsqueeze(-1)
+    return span_emb, span_mask
+
+
+def self_att_representation(x: Tensor, score: Tensor, mask: Tensor) -> Tensor:
+    """get_self_att_representation (:174-181): softmax(score + (1-mask) * -10000) weighted sum."""
+    m = (1.0 - mask.to(score.dtype)) * -10000.0
+    prob = torch.softmax(score + m, dim=-1).unsqueeze(-1)
+    return (prob * x).sum(1)
+
+
+def distant_cross_entropy(logits: Tensor, positions: Tensor) -> Tensor:
+    """distant_cross_entropy without mask (:183-192)."""
+    lp = torch.log_softmax(logits, dim=-1)
+    pos = positions.to(lp.dtype)
+    return -torch.mean((pos * lp).sum(-1) / pos.sum(-1))
+
+
+def tvnet_forward(p, cfg: EncoderCfg, batch: Dict[str, Tensor], *, use_prefix=True, use_probe=True, beta=0.5,
+                  num_epochs=30):
+    """Eval-mode restatement of TVNetSAModel.forward (models/bert_model.py:246-321; no GCN, no Cutoff).
+
+    batch: input_ids, attention_mask, token_type_ids [B,L]; start_positions / end_positions [B,L] (multi-hot);
+    span_starts / span_ends [B,M]; polarity_labels / label_masks [B,M]; images / aux_imgs with use_prefix.
+    Returns dict(loss, tot_loss, prob_loss, start_logits, end_logits, ac_logits, logits)."""
+    ids, am, tt = batch["input_ids"], batch["attention_mask"], batch["token_type_ids"]
+    B = ids.shape[0]
+    pkv = None
+    if use_prefix:
+        pkv, _, _ = visual_prompt(p, batch["images"], batch["aux_imgs"], None, vao=False,
+                                  n_layers=cfg.num_hidden_layers, hidden=cfg.hidden_size,
+                                  n_heads=cfg.num_attention_heads)               # :379-414 (no ANP heads)
+        P = pkv[0][0].shape[2]
+        full_mask = torch.cat([torch.ones(B, P), am.to(torch.float32)], dim=1)   # :257-259
+    else:
+        full_mask = am
+    enc = encoder_forward(p, cfg, ids, full_mask, tt, pkv)
+    seq = enc["last_hidden_state"]                                               # dropout = identity in eval
+    ae = F.linear(seq, p["binary_affine.weight"], p["binary_affine.bias"])      # :351
+    start_logits, end_logits = ae[..., 0], ae[..., 1]
+    span_emb, span_mask = span_representation(batch["span_starts"], batch["span_ends"], seq, am)   # :364
+    score = F.linear(span_emb, p["unary_affine.weight"], p["unary_affine.bias"]).squeeze(-1)       # :367-368
+    pooled = self_att_representation(span_emb, score, span_mask)                 # :369
+    pooled = torch.tanh(F.linear(pooled, p["dense.weight"], p["dense.bias"]))    # :371-372
+    ac_logits = F.linear(pooled, p["classifier.weight"], p["classifier.bias"])   # :374
+    flat_labels = batch["polarity_labels"].reshape(-1)
+    flat_masks = batch["label_masks"].reshape(-1).to(ac_logits.dtype)
+    start_loss = distant_cross_entropy(start_logits, batch["start_positions"])   # :298-300
+    end_loss = distant_cross_entropy(end_logits, batch["end_positions"])
+    ae_loss = (start_loss + end_loss) / 2
+    ac_loss = F.cross_entropy(ac_logits, flat_labels)                            # mean over all spans (:302)
+    ac_loss = torch.sum(flat_masks * ac_loss) / flat_masks.sum()                 # :303 (a scalar times mask: no-op)
+    tot = ae_loss + ac_loss
+    out = {"start_logits": start_logits, "end_logits": end_logits, "ac_logits": ac_logits,
+           "logits": ac_logits.view(B, -1, ac_logits.shape[-1]), "tot_loss": tot,
+           "hidden_states": enc["hidden_states"]}
+    if use_probe:
+        pl, norms, labels = probe_loss(enc["hidden_states"][7], p["oneWordpsdProbe.oneWordpsdProbe.proj"])   # :356
+        out.update(prob_loss=pl, loss=combine_loss(tot, pl, beta, num_epochs))   # :312
+    else:
+        out["loss"] = tot
+    return out
