@@ -90,10 +90,13 @@ int mtvaf_skinny_linear_f32(const float* x, int64_t ldx, const float* w, int64_t
                             int K, float* out, int64_t ldo, void* stream);
 
 /* backward of the skinny layer (N <= 16).  dgrad: dx[m,k] = keep(seed, m*K+k)/(1-p) * sum_n dy[m,n] w[n,k], i.e. with
- * the dropout that precedes the tag head (bert_model.py:506) applied to the result, written as dx_dtype;
+ * the dropout that precedes the tag head (bert_model.py:506) applied to the result, written as dx_dtype; when
+ * `tanh_out` (same dtype / leading dim as dx) is given the result is also multiplied by 1 - tanh_out^2 (the
+ * layer's input was tanh(dense(.)), bert_model.py:371-374);
  * wgrad: dw[n,k] += sum_m dy[m,n] x[m,k] (fp32 atomics), N*K/8 <= 1536. */
 int mtvaf_skinny_linear_dgrad(const float* dy, int64_t lddy, const float* w, int64_t ldw, int M, int N, int K,
-                              float p_drop, uint64_t seed, void* dx, int64_t lddx, int dx_dtype, void* stream);
+                              float p_drop, uint64_t seed, void* dx, int64_t lddx, int dx_dtype, const void* tanh_out,
+                              void* stream);
 int mtvaf_skinny_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, int M, int N, int K,
                               float* dw, int64_t lddw, void* stream);
 
@@ -220,6 +223,29 @@ int mtvaf_crf_nll_fwd_bwd(const float* emissions, const int64_t* tags, const int
 /* Viterbi: best_tags [B, L] int64 (positions >= length are -1), lengths [B] int64 */
 int mtvaf_crf_decode(const float* emissions, const int64_t* mask, const float* start, const float* end,
                      const float* trans, int B, int L, int T, int64_t* best_tags, int64_t* lengths, void* stream);
+
+/* ---- span variant TVNetSAModel: models/bert_model.py:113-190, 323-376 ------------------------- */
+/* workspace (int32 [2B+1]) := sentence lengths, exclusive prefix sums, total tokens of the compacted stream
+ * (get_span_representation :149-152; attention masks are left-aligned). B <= 1024. */
+int mtvaf_span_offsets(const int64_t* attention_mask, int B, int L, int32_t* workspace, void* stream);
+/* get_span_representation + unary_affine + get_self_att_representation (:147-181, :364-369):
+ * pooled[s, :] = sum_j softmax_j(row_j . w + b) row_j over the span's rows of the compacted token stream
+ * (span s = (n, m): stream elements offset[n] + start .. + end, clamped to the last element).  seq: [B*L, H] fp32. */
+int mtvaf_span_pool_fwd(const float* seq, const int32_t* workspace, const int64_t* span_starts,
+                        const int64_t* span_ends, const float* w_unary, const float* b_unary, int B, int L, int M,
+                        int H, float* pooled, void* stream);
+/* backward: d_seq (fp32 [B*L, H]), d_w_unary [H], d_b_unary [1] are ACCUMULATED (atomics). */
+int mtvaf_span_pool_bwd(const float* d_pooled, const float* seq, const int32_t* workspace, const int64_t* span_starts,
+                        const int64_t* span_ends, const float* w_unary, const float* b_unary, int B, int L, int M,
+                        int H, float* d_seq, float* d_w_unary, float* d_b_unary, void* stream);
+/* distant_cross_entropy (:183-192, no mask): loss[0] += scale * mean_b(-sum_l pos log_softmax(x)_l / sum_l pos);
+ * logits / dlogits are read / written with an element `stride` (start and end logits are the two columns of the
+ * binary_affine output [B*L, 2], :351-354); dlogits (optional) = d(scale * loss)/d logits. */
+int mtvaf_distant_ce_fwd_bwd(const float* logits, int64_t stride, const int64_t* positions, int B, int L, float scale,
+                             float* loss, float* dlogits, void* stream);
+/* nn.CrossEntropyLoss() (mean) over N rows of C classes (:296,302): loss[0] += scale * mean; dlogits optional. */
+int mtvaf_ce_mean_fwd_bwd(const float* logits, const int64_t* labels, int N, int C, float scale, float* loss,
+                          float* dlogits, void* stream);
 
 /* ---- loss combination: probes/loss.py:13-18 + bert_model.py:523-525 without the .item() sync --- */
 /* out[0] = crf_nll_sum/B + (prob_loss > 0.1 ? prob_loss * beta * 2^-epoch : 0) + alpha * img_loss;

@@ -4,7 +4,7 @@ Importing the package loads the CUDA extension (mtvaf_b200/_C/libmtvaf_b200.so) 
 is missing: there is no CPU or PyTorch fallback.  `mtvaf_b200.synthetic` (pure torch-CPU data
 generation) can be imported on its own without the extension.
 """
-__all__ = ["RobertaModel", "BertModel", "TVNetSAModel2", "CRF", "probe", "OneWordPSDProbe", "TwoWordPSDProbe",
+__all__ = ["RobertaModel", "BertModel", "TVNetSAModel", "TVNetSAModel2", "CRF", "probe", "OneWordPSDProbe", "TwoWordPSDProbe",
            "ConstructLabelGaget", "CombineLoss", "FeatureStub", "ImageModel"]
 
 

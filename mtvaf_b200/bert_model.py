@@ -1,2 +1,2 @@
 """Name-compatible alias of the reference's models/bert_model.py."""
-from .modules import TVNetSAModel2, ImageModel, FeatureStub, CRF, TokenClassifierOutput  # noqa: F401
+from .modules import TVNetSAModel, TVNetSAModel2, ImageModel, FeatureStub, CRF, TokenClassifierOutput  # noqa: F401

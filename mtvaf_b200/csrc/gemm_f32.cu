@@ -163,8 +163,9 @@ skinny_linear_kernel(const float* __restrict__ x, long long ldx, const float* __
 template <typename TO, int NT>
 __global__ void __launch_bounds__(256)
 skinny_dgrad_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ w, long long ldw, int M,
-                    int N, int K, TO* __restrict__ dx, long long lddx, uint32_t drop_thr, float drop_scale,
-                    unsigned long long seed_in, const unsigned long long* __restrict__ step) {
+                    int N, int K, TO* __restrict__ dx, long long lddx, const TO* __restrict__ tanh_out,
+                    uint32_t drop_thr, float drop_scale, unsigned long long seed_in,
+                    const unsigned long long* __restrict__ step) {
   const unsigned long long seed = drop_thr ? step_seed(seed_in, step) : seed_in;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -188,6 +189,11 @@ skinny_dgrad_kernel(const float* __restrict__ dy, long long lddy, const float* _
         acc.y = dropout_keep(seed, i0 + 1, drop_thr) ? acc.y * drop_scale : 0.f;
         acc.z = dropout_keep(seed, i0 + 2, drop_thr) ? acc.z * drop_scale : 0.f;
         acc.w = dropout_keep(seed, i0 + 3, drop_thr) ? acc.w * drop_scale : 0.f;
+      }
+      if (tanh_out) {                                  // the layer's input was tanh(.): multiply by 1 - tanh^2
+        const TO* t = tanh_out + (long long)m * lddx + k;
+        const float t0 = to_f<TO>(t[0]), t1 = to_f<TO>(t[1]), t2 = to_f<TO>(t[2]), t3 = to_f<TO>(t[3]);
+        acc.x *= 1.f - t0 * t0; acc.y *= 1.f - t1 * t1; acc.z *= 1.f - t2 * t2; acc.w *= 1.f - t3 * t3;
       }
       TO* o = dx + (long long)m * lddx + k;
       if constexpr (sizeof(TO) == 4) {
@@ -327,7 +333,7 @@ extern "C" int mtvaf_skinny_linear_f32(const float* x, int64_t ldx, const float*
 
 extern "C" int mtvaf_skinny_linear_dgrad(const float* dy, int64_t lddy, const float* w, int64_t ldw, int M, int N,
                                          int K, float p_drop, uint64_t seed, void* dx, int64_t lddx, int dx_dtype,
-                                         void* stream) {
+                                         const void* tanh_out, void* stream) {
   MTVAF_REQUIRE(dy && w && dx && M > 0 && N > 0 && K > 0, "skinny_linear_dgrad: bad argument");
   MTVAF_REQUIRE(N <= 16, "skinny_linear_dgrad: N=%d > 16 (use mtvaf_gemm_f32)", N);
   MTVAF_REQUIRE(K % 4 == 0 && ldw % 4 == 0 && lddx % 4 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0 &&
@@ -347,10 +353,12 @@ extern "C" int mtvaf_skinny_linear_dgrad(const float* dy, int64_t lddy, const fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dx_dtype == MTVAF_BF16)
     skinny_dgrad_kernel<__nv_bfloat16, 16><<<(int)blocks, 256, 0, st>>>(dy, lddy, w, ldw, M, N, K, (__nv_bfloat16*)dx,
-                                                                        lddx, thr, scale, seed, step_source());
+                                                                        lddx, (const __nv_bfloat16*)tanh_out, thr,
+                                                                        scale, seed, step_source());
   else
-    skinny_dgrad_kernel<float, 16><<<(int)blocks, 256, 0, st>>>(dy, lddy, w, ldw, M, N, K, (float*)dx, lddx, thr,
-                                                                scale, seed, step_source());
+    skinny_dgrad_kernel<float, 16><<<(int)blocks, 256, 0, st>>>(dy, lddy, w, ldw, M, N, K, (float*)dx, lddx,
+                                                                (const float*)tanh_out, thr, scale, seed,
+                                                                step_source());
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

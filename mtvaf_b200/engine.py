@@ -565,3 +565,103 @@ class Engine:
             dx7 = ops.gemm(dT, projc, M=T, N=H, K=Tm.shape[1], out_dtype=self.compute_dtype)
             grads[saved["probe_layer"]] = dx7
         return grads
+
+
+# =================================================================================================
+# span variant heads: TVNetSAModel.extraction / classification / losses (models/bert_model.py:288-376)
+# =================================================================================================
+def _span_heads_fwd(self, hs: List[torch.Tensor], B: int, Lq: int, mask: torch.Tensor, batch: Dict[str, torch.Tensor],
+                    use_probe: bool, beta: float, epoch: int, training: bool, save: bool, probe_layer: int = 7):
+    """batch: start_positions / end_positions [B,L], span_starts / span_ends [B,M], polarity_labels [B,M] (int64)
+    or None entries for inference.  Returns (out dict, saved)."""
+    c, f = self.cfg, self.flat
+    T, H = B * Lq, c.H
+    cd = self.compute_dtype
+    seq = hs[c.n_layers]
+    seq32 = ops.cast_f32(seq) if seq.dtype == BF16 else seq
+    p_d = 0.1 if training else 0.0                                             # self.dropout, bert_model.py:237,349
+    seq_d = ops.dropout_apply(seq32, p_d, self.seed(910)) if p_d > 0 else seq32
+    ae = ops.skinny_linear(seq_d, f.w("binary_affine.weight"), f.w("binary_affine.bias"))      # [T,2]  :351
+    out = dict(ae=ae, start_logits=ae.view(B, Lq, 2)[..., 0], end_logits=ae.view(B, Lq, 2)[..., 1], loss=None,
+               prob_loss=None, sequence_output=seq_d)
+    saved = dict(B=B, L=Lq, seq_d=seq_d, p_d=p_d, seed_d=self.seed(910), use_probe=use_probe, probe_layer=probe_layer)
+    starts, ends = batch.get("span_starts"), batch.get("span_ends")
+    if starts is not None:
+        M = starts.shape[1]
+        ws = ops.span_offsets(mask)
+        w_u = f.w("unary_affine.weight").view(-1)
+        pooled = ops.span_pool_fwd(seq_d, ws, starts, ends, w_u, f.w("unary_affine.bias"), B, Lq)   # :364-369
+        pooled_c = ops.cast_bf16(pooled) if cd == BF16 else pooled
+        h_t = ops.linear_fwd(pooled_c, self.cw("dense.weight"), f.w("dense.bias"), mode=L.EPI_TANH)  # :371-372
+        h_d = ops.dropout_apply(h_t, p_d, self.seed(911)) if p_d > 0 else h_t
+        h32 = ops.cast_f32(h_d) if h_d.dtype == BF16 else h_d
+        ac = ops.skinny_linear(h32, f.w("classifier.weight"), f.w("classifier.bias"))             # [B*M,4] :374
+        out.update(ac_logits=ac, logits=ac.view(B, M, -1))
+        saved.update(ws=ws, starts=starts, ends=ends, pooled_c=pooled_c, h_t=h_t, h32=h32, seed_h=self.seed(911), M=M)
+    prob_loss = None
+    if use_probe:
+        x7 = hs[probe_layer]
+        proj = f.params["oneWordpsdProbe.oneWordpsdProbe.proj"]
+        r = proj.shape[1]
+        norms = torch.zeros(T, dtype=F32, device=seq.device)
+        projc = self.cw("oneWordpsdProbe.oneWordpsdProbe.proj")
+        Tm = torch.empty((T, r), dtype=x7.dtype, device=seq.device)
+        ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H, mode=L.EPI_SQNORM, rowvec=norms, out=Tm)
+        plabels = ops.probe_labels(norms.view(B, Lq))
+        prob_loss, dnorms = ops.mse(norms, plabels.view(-1), save)
+        out.update(prob_loss=prob_loss, norms=norms.view(B, Lq), pseudo_labels=plabels)
+        saved.update(Tm=Tm, dnorms=dnorms, x7=x7)
+    sp, ep, pol = batch.get("start_positions"), batch.get("end_positions"), batch.get("polarity_labels")
+    if sp is not None and ep is not None and pol is not None and starts is not None:
+        tot = torch.zeros(1, dtype=F32, device=seq.device)
+        d_ae = torch.empty_like(ae) if save else None
+        ops.distant_ce(ae, 0, sp, 0.5, tot, d_ae)                               # (start_loss + end_loss) / 2  :298-300
+        ops.distant_ce(ae, 1, ep, 0.5, tot, d_ae)
+        d_ac = ops.ce_mean(out["ac_logits"], pol.reshape(-1).contiguous(), 1.0, tot, save)   # :302-303
+        loss, flag = ops.combine_loss(tot, 1, prob_loss, beta, epoch, None, 0.0)             # :312
+        out.update(loss=loss, tot_loss=tot)
+        saved.update(d_ae=d_ae, d_ac=d_ac, flag=flag, probe_coef=beta * 2.0 ** (-epoch))
+    return out, (saved if save else None)
+
+
+def _span_heads_bwd(self, saved, dloss: torch.Tensor):
+    c, f = self.cfg, self.flat
+    B, Lq, H = saved["B"], saved["L"], c.H
+    T = B * Lq
+    cd = self.compute_dtype
+    grads = {}
+    d_ae, d_ac = saved["d_ae"], saved["d_ac"]
+    ops.scale_by_device_scalar(d_ae, dloss)
+    ops.scale_by_device_scalar(d_ac, dloss)
+    # classifier <- dropout <- tanh <- dense <- pooled
+    ops.skinny_linear_wgrad(d_ac, saved["h32"], f.g("classifier.weight"))
+    ops.colsum(d_ac, f.g("classifier.bias"))
+    d_pre = ops.skinny_linear_dgrad(d_ac, f.w("classifier.weight"), cd, saved["p_d"], saved["seed_h"],
+                                    tanh_out=saved["h_t"])                         # [B*M,H]
+    ops.linear_wgrad(d_pre, saved["pooled_c"], f.g("dense.weight"))
+    ops.colsum(d_pre, f.g("dense.bias"))
+    d_pooled = ops.gemm(d_pre, self.cw("dense.weight"), b_mn=True, M=d_pre.shape[0], N=H, K=H, out_dtype=F32)
+    # binary_affine, then the span gather scatters on top of it
+    d_seq = ops.skinny_linear_dgrad(d_ae, f.w("binary_affine.weight"), F32)
+    ops.skinny_linear_wgrad(d_ae, saved["seq_d"], f.g("binary_affine.weight"))
+    ops.colsum(d_ae, f.g("binary_affine.bias"))
+    ops.span_pool_bwd(d_pooled, saved["seq_d"], saved["ws"], saved["starts"], saved["ends"],
+                      f.w("unary_affine.weight").view(-1), f.w("unary_affine.bias"), B, Lq, d_seq,
+                      f.g("unary_affine.weight").view(-1), f.g("unary_affine.bias"))
+    if saved["p_d"] > 0:
+        d_seq = ops.dropout_apply(d_seq, saved["p_d"], saved["seed_d"])
+    grads[c.n_layers] = ops.cast_bf16(d_seq) if cd == BF16 else d_seq
+    if saved["use_probe"]:
+        dn = saved["dnorms"]
+        ops.scale_by_device_scalar(dn, dloss)
+        ops.scale_by_device_scalar(dn, saved["flag"].to(F32))
+        Tm, x7 = saved["Tm"], saved["x7"]
+        dT = ops.rowscale(Tm, dn, 2.0 * saved["probe_coef"])
+        ops.linear_wgrad(x7, dT, f.g("oneWordpsdProbe.oneWordpsdProbe.proj"))
+        projc = self.cw("oneWordpsdProbe.oneWordpsdProbe.proj")
+        grads[saved["probe_layer"]] = ops.gemm(dT, projc, M=T, N=H, K=Tm.shape[1], out_dtype=cd)
+    return grads
+
+
+Engine.span_heads_fwd = _span_heads_fwd
+Engine.span_heads_bwd = _span_heads_bwd

@@ -37,7 +37,7 @@ SIGNATURES = {
     "mtvaf_set_gemm_impl": [_i],
     "mtvaf_gemm_f32": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
     "mtvaf_skinny_linear_f32": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp],
-    "mtvaf_skinny_linear_dgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _u64, _vp, _i64, _i, _vp],
+    "mtvaf_skinny_linear_dgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _u64, _vp, _i64, _i, _vp, _vp],
     "mtvaf_skinny_linear_wgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp],
     "mtvaf_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mtvaf_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
@@ -67,6 +67,11 @@ SIGNATURES = {
     "mtvaf_pairwise_sqdist": [_vp, _i64, _i, _i, _i, _i, _vp, _vp],
     "mtvaf_crf_nll_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
     "mtvaf_crf_decode": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "mtvaf_span_offsets": [_vp, _i, _i, _vp, _vp],
+    "mtvaf_span_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "mtvaf_span_pool_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mtvaf_distant_ce_fwd_bwd": [_vp, _i64, _vp, _i, _i, _f, _vp, _vp, _vp],
+    "mtvaf_ce_mean_fwd_bwd": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp],
     "mtvaf_combine_loss": [_vp, _i, _vp, _f, _i, _vp, _i, _f, _vp, _vp, _vp],
     "mtvaf_adamw_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i, _vp, _vp],
     "mtvaf_adam_dyn_advance": [_vp, _f, _f, _i, _i, _vp],

@@ -780,6 +780,206 @@ class TVNetSAModel2(nn.Module):
         return res
 
 
+class _SpanHeadsFn(torch.autograd.Function):
+    """Heads + losses of the span variant (models/bert_model.py:288-312, 323-376) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, engine: Engine, model, hs_probe, hs_last, mask, batch, training):
+        a = model.args
+        B, Lq = mask.shape
+        H = engine.cfg.H
+        n = engine.cfg.n_layers
+        probe_layer = min(7, n)
+        hs = {n: hs_last.reshape(B * Lq, H), probe_layer: None}
+        if hs_probe is not None:
+            hs[probe_layer] = hs_probe.reshape(B * Lq, H)
+        use_probe = bool(getattr(a, "use_probe", False)) and hs_probe is not None
+        need_grad = any(ctx.needs_input_grad) and batch.get("polarity_labels") is not None
+        out, saved = engine.span_heads_fwd(hs, B, Lq, mask, batch, use_probe, float(getattr(a, "beta", 0.5)),
+                                           int(getattr(a, "num_epochs", 30)), training, need_grad,
+                                           probe_layer=probe_layer)
+        ctx.engine, ctx.saved = engine, saved
+        ctx.shape = hs_last.shape
+        ctx.has_probe_in = hs_probe is not None
+        model._last_heads = out
+        dev = mask.device
+        loss = out["loss"] if out["loss"] is not None else torch.zeros(1, dtype=F32, device=dev)
+        prob = out["prob_loss"] if out["prob_loss"] is not None else torch.zeros(1, dtype=F32, device=dev)
+        tot = out.get("tot_loss")
+        tot = tot if tot is not None else torch.zeros(1, dtype=F32, device=dev)
+        ctx.mark_non_differentiable(prob, tot)
+        return loss.view(()), prob.view(()), tot.view(())
+
+    @staticmethod
+    def backward(ctx, dloss, _dprob, _dtot):
+        eng = ctx.engine
+        if ctx.saved is None:
+            raise L.MtvafError("backward through the span heads needs the training labels (no loss was computed)")
+        eng.flat.attach_grads()
+        grads = eng.span_heads_bwd(ctx.saved, dloss.reshape(1).to(F32).contiguous())
+        n = eng.cfg.n_layers
+        d_last = grads[n].view(ctx.shape)
+        pl = ctx.saved["probe_layer"]
+        d_probe = grads[pl].view(ctx.shape) if (ctx.has_probe_in and pl in grads and pl != n) else None
+        ctx.saved = None
+        return (None, None, d_probe, d_last, None, None, None)
+
+
+class TVNetSAModel(nn.Module):
+    """Span variant (models/bert_model.py:192-414; `--dataset_name twitter15|twitter17`, MTVAF_training.py:32-50):
+    same encoder + visual prefix (no ANP heads), span extractor (`binary_affine`), span-pooled polarity classifier
+    (`unary_affine`, `dense`, `classifier`), distant / mean cross-entropy losses.  GCN extras
+    (`gcn_layer_number`, `num_layers`) and Cutoff augmentation are out of scope."""
+
+    def __init__(self, label_list, tokenizer, args, type_num=None, use_weight=False, config=None,
+                 image_model: Optional[nn.Module] = None):
+        super().__init__()
+        if getattr(args, "gcn_layer_number", 0) > 0 or getattr(args, "num_layers", 0) > 0:
+            raise L.MtvafError("mtvaf_b200.TVNetSAModel: the GCN extras are outside the hot path (SURVEY.md 2, row 6)")
+        self.args = args
+        self.type_num = type_num
+        self.tokenizer = tokenizer
+        self.prefix_dim = args.prefix_dim
+        self.prefix_len = args.prefix_len
+        enc_cls = RobertaModel if "roberta" in args.bert_name else BertModel
+        self.bert = enc_cls.from_config(config) if config is not None else enc_cls.from_pretrained(args.bert_name)
+        H = self.bert.config.hidden_size
+        nl = self.bert.config.num_hidden_layers
+        # registration order of models/bert_model.py:205-240 (checkpoints are walked by index, train.py:495-521)
+        self.dense = nn.Linear(H, H)
+        self.activation = nn.Tanh()
+        self.unary_affine = nn.Linear(H, 1)
+        self.binary_affine = nn.Linear(H, 2)
+        self.num_labels = len(label_list) + 1
+        self.classifier = nn.Linear(H, 4)
+        if args.use_prefix:
+            if image_model is not None:
+                self.image_model = image_model
+            else:
+                self.image_model = ImageModel(use_152=getattr(args, "use_152", False),
+                                              use_101=getattr(args, "use_101", False),
+                                              use_34=getattr(args, "use_34", False),
+                                              use_18=getattr(args, "use_18", False), resnet_root=args.resnet_root)
+            self.encoder_conv = nn.Sequential(nn.Linear(3840, 800), nn.Tanh(), nn.Linear(800, 4 * 2 * H))
+            self.projectors = nn.ModuleList([nn.Linear(4 * H * 2, 4) for _ in range(nl)])
+        self.fc = nn.Linear(H, self.num_labels)          # registered by the reference (:236), unused on this path
+        self.dropout = nn.Dropout(0.1)
+        if args.use_probe:
+            self.oneWordpsdProbe = probe(args={"probe": {"maximum_rank": H // 2}, "model": {"hidden_dim": H}})
+            self.combineLoss = CombineLoss(args.beta)
+        self._engine: Optional[Engine] = None
+        self._compute_dtype = _resolve_dtype(getattr(args, "compute_dtype", None))
+        self.bert._engine_owner = self.engine
+        self._last_heads = None
+
+    def set_compute_dtype(self, dtype):
+        self._compute_dtype = _resolve_dtype(dtype)
+        if self._engine is not None:
+            self._engine.compute_dtype = self._compute_dtype
+
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self, self.bert.hot_config(), "bert.", self._compute_dtype)
+        return self._engine
+
+    _features = TVNetSAModel2._features
+
+    def get_visual_prompt(self, images, aux_imgs):
+        """models/bert_model.py:379-414 (the gate stack without the ANP heads); returns the packed prefix."""
+        eng = self.engine()
+        eng.prepare()
+        feats = self._features(images, aux_imgs)
+        kv, _ = _FusionFn.apply(eng, feats, None, False, self.training, 3, _grad_anchor(self.dense.weight))
+        return kv
+
+    def _encode(self, input_ids, attention_mask, token_type_ids, prefix_guids):
+        return self.bert(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids,
+                         past_key_values=prefix_guids, output_attentions=True, output_hidden_states=True,
+                         return_dict=True)
+
+    def extraction(self, prompt_attention_mask, input_ids, prefix_guids, token_type_ids, augument=False, labels=None,
+                   adj_matrix=None, src_mask=None, aspect_mask=None):
+        """models/bert_model.py:323-361, inference form (no autograd through this entry point: the trainer calls it
+        to propose spans, modules/train.py:362-380; training goes through forward()).  `prompt_attention_mask` is
+        [B, P+L] as in the reference; the text part is its last L columns."""
+        if augument:
+            raise L.MtvafError("Cutoff augmentation is outside the hot path (SURVEY.md 2, row 12)")
+        eng = self.engine()
+        eng.prepare()
+        B, Lq = input_ids.shape
+        text_mask = prompt_attention_mask[:, -Lq:].to(torch.long).contiguous()
+        with torch.no_grad():
+            out = self._encode(input_ids, text_mask, token_type_ids, prefix_guids)
+            hs = out["hidden_states"]
+            nl = self.bert.config.num_hidden_layers
+            use_probe = bool(getattr(self.args, "use_probe", False))
+            H = eng.cfg.H
+            hsd = {nl: hs[nl].reshape(B * Lq, H), min(7, nl): hs[min(7, nl)].reshape(B * Lq, H)}
+            o, _ = eng.span_heads_fwd(hsd, B, Lq, text_mask, {}, use_probe, float(getattr(self.args, "beta", 0.5)),
+                                      int(getattr(self.args, "num_epochs", 30)), self.training, False,
+                                      probe_layer=min(7, nl))
+        seq = o["sequence_output"].view(B, Lq, H)
+        if use_probe:
+            return o["start_logits"], o["end_logits"], seq, o["prob_loss"].view(())
+        return o["start_logits"], o["end_logits"], seq
+
+    def classification(self, span_starts, span_ends, sequence_input, attention_mask):
+        """models/bert_model.py:363-376, inference form: (logits [B,M,4], ac_logits [B*M,4])."""
+        eng = self.engine()
+        eng.prepare()
+        B, Lq, H = sequence_input.shape
+        f = eng.flat
+        with torch.no_grad():
+            seq = sequence_input.reshape(B * Lq, H)
+            seq32 = (ops.cast_f32(seq.contiguous()) if seq.dtype == BF16 else seq.to(F32)).contiguous()
+            mask = attention_mask.to(torch.long).contiguous()
+            ws = ops.span_offsets(mask)
+            pooled = ops.span_pool_fwd(seq32, ws, span_starts.contiguous(), span_ends.contiguous(),
+                                       f.w("unary_affine.weight").view(-1), f.w("unary_affine.bias"), B, Lq)
+            pc = ops.cast_bf16(pooled) if eng.bf16 else pooled
+            h = ops.linear_fwd(pc, eng.cw("dense.weight"), f.w("dense.bias"), mode=L.EPI_TANH)
+            h32 = ops.cast_f32(h) if h.dtype == BF16 else h
+            ac = ops.skinny_linear(h32, f.w("classifier.weight"), f.w("classifier.bias"))
+        return ac.view(B, span_starts.shape[1], -1), ac
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, start_positions=None,
+                end_positions=None, span_starts=None, span_ends=None, polarity_labels=None, label_masks=None,
+                images=None, aux_imgs=None, valid_ids=None, adjacency_matrix=None, output_attention=False,
+                augument=False, labels=None, adj_matrix=None, src_mask=None, aspect_mask=None, polaritys=None):
+        """models/bert_model.py:246-321.  `label_masks` is accepted and -- exactly as in the reference, where the
+        already-averaged cross-entropy is multiplied by the mask and divided by its sum (:302-303) -- has no
+        effect on the loss."""
+        if not input_ids.is_cuda:
+            raise L.MtvafError("mtvaf_b200 runs on CUDA devices only (no CPU fallback); got %s" % input_ids.device)
+        if augument:
+            raise L.MtvafError("Cutoff augmentation is outside the hot path (SURVEY.md 2, row 12)")
+        eng = self.engine()
+        eng.step_counter += 1
+        eng.prepare()
+        eng._nested = True
+        try:
+            a = self.args
+            kv = self.get_visual_prompt(images, aux_imgs) if a.use_prefix else None
+            mask = attention_mask.to(torch.long).contiguous()
+            out = self._encode(input_ids, mask, token_type_ids, kv)
+            hs = out["hidden_states"]
+            nl = self.bert.config.num_hidden_layers
+            use_probe = bool(getattr(a, "use_probe", False))
+            lab = lambda t: None if t is None else t.to(torch.long).contiguous()
+            batch = dict(start_positions=lab(start_positions), end_positions=lab(end_positions),
+                         span_starts=lab(span_starts), span_ends=lab(span_ends), polarity_labels=lab(polarity_labels))
+            loss, prob, tot = _SpanHeadsFn.apply(eng, self, hs[min(7, nl)] if use_probe else None, hs[nl], mask, batch,
+                                                 self.training)
+            heads = self._last_heads
+            has_loss = heads["loss"] is not None
+            res = TokenClassifierOutput(loss=loss if has_loss else None, logits=heads.get("logits"))
+            if use_probe:
+                return res, prob, tot
+            return res
+        finally:
+            eng._nested = False
+
+
 class _DecodedTags(list):
     """CRF decode result: behaves as the reference's List[List[int]] (models/bert_model.py:511) but the
     device->host copy happens only when the list is first read (no sync in the training step)."""

@@ -154,15 +154,18 @@ def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
 
 
 def skinny_linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out_dtype: torch.dtype, p_drop: float = 0.0,
-                        seed: int = 0) -> torch.Tensor:
-    """dx = dropout_mask(seed) * (dy w) / (1-p) for N = w.shape[0] <= 16, written in `out_dtype`."""
-    _cuda(dy, w)
+                        seed: int = 0, tanh_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = dropout_mask(seed) * (dy w) / (1-p) [* (1 - tanh_out^2)] for N = w.shape[0] <= 16, in `out_dtype`."""
+    _cuda(dy, w, tanh_out)
     assert dy.dtype == torch.float32 and w.dtype == torch.float32 and dy.stride(1) == 1 and w.stride(1) == 1
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty((M, K), dtype=out_dtype, device=dy.device)
+    if tanh_out is not None:
+        assert tanh_out.dtype == out_dtype and tanh_out.shape == dx.shape and tanh_out.is_contiguous()
     _check(_raw.mtvaf_skinny_linear_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), M, N, K, p_drop,
-                                          seed, dx.data_ptr(), dx.stride(0), dt(dx), _stream()), "skinny_linear_dgrad")
+                                          seed, dx.data_ptr(), dx.stride(0), dt(dx), _p(tanh_out), _stream()),
+           "skinny_linear_dgrad")
     return dx
 
 
@@ -422,6 +425,48 @@ def crf_decode(em, mask, start, end, trans):
     _check(_raw.mtvaf_crf_decode(em.data_ptr(), mask.data_ptr(), start.data_ptr(), end.data_ptr(), trans.data_ptr(),
                                  B, Lq, T, best.data_ptr(), lens.data_ptr(), _stream()), "crf_decode")
     return best, lens
+
+
+# ------------------------------------------------------------------------------------------ span variant heads
+def span_offsets(mask):
+    B, Lq = mask.shape
+    ws = torch.empty(2 * B + 1, dtype=torch.int32, device=mask.device)
+    _check(_raw.mtvaf_span_offsets(mask.data_ptr(), B, Lq, ws.data_ptr(), _stream()), "span_offsets")
+    return ws
+
+
+def span_pool_fwd(seq, ws, starts, ends, w_u, b_u, B, Lq):
+    M = starts.shape[1]
+    H = seq.shape[1]
+    assert seq.dtype == torch.float32 and seq.is_contiguous()
+    pooled = torch.empty((B * M, H), dtype=torch.float32, device=seq.device)
+    _check(_raw.mtvaf_span_pool_fwd(seq.data_ptr(), ws.data_ptr(), starts.data_ptr(), ends.data_ptr(), w_u.data_ptr(),
+                                    b_u.data_ptr(), B, Lq, M, H, pooled.data_ptr(), _stream()), "span_pool_fwd")
+    return pooled
+
+
+def span_pool_bwd(d_pooled, seq, ws, starts, ends, w_u, b_u, B, Lq, d_seq, d_w, d_b):
+    M = starts.shape[1]
+    H = seq.shape[1]
+    _check(_raw.mtvaf_span_pool_bwd(d_pooled.data_ptr(), seq.data_ptr(), ws.data_ptr(), starts.data_ptr(),
+                                    ends.data_ptr(), w_u.data_ptr(), b_u.data_ptr(), B, Lq, M, H, d_seq.data_ptr(),
+                                    d_w.data_ptr(), d_b.data_ptr(), _stream()), "span_pool_bwd")
+
+
+def distant_ce(logits2, col, positions, scale, loss, dlogits2):
+    """logits2: [B*L, 2] fp32 (binary_affine output); col 0 = start, 1 = end. Accumulates into loss[0]."""
+    B, Lq = positions.shape
+    d = None if dlogits2 is None else dlogits2.data_ptr() + 4 * col
+    _check(_raw.mtvaf_distant_ce_fwd_bwd(logits2.data_ptr() + 4 * col, logits2.stride(0), positions.data_ptr(), B, Lq,
+                                         scale, loss.data_ptr(), d, _stream()), "distant_ce")
+
+
+def ce_mean(logits, labels, scale, loss, want_grad):
+    N, Cc = logits.shape
+    d = torch.empty_like(logits) if want_grad else None
+    _check(_raw.mtvaf_ce_mean_fwd_bwd(logits.data_ptr(), labels.data_ptr(), N, Cc, scale, loss.data_ptr(), _p(d),
+                                      _stream()), "ce_mean")
+    return d
 
 
 def combine_loss(crf_nll_sum, B, prob_loss, beta, epoch, img_losses, alpha):

@@ -27,6 +27,7 @@ CASES = {
     "tvnet2_roberta": dict(kind="roberta", B=4, L=32, shape="twitter2015", batch_seed=11, param_seed=101),
     "encoder_roberta_p36": dict(kind="roberta", B=2, L=48, shape="twitter2017", batch_seed=12, param_seed=102, P=36),
     "encoder_bert": dict(kind="bert", B=2, L=40, shape="twitter2015", batch_seed=13, param_seed=103),
+    "tvnet_span_roberta": dict(kind="roberta", B=4, L=32, shape="twitter2015", batch_seed=14, param_seed=104, M=6),
 }
 
 
@@ -93,6 +94,30 @@ def gen_tvnet2(name, c):
     }
     torch.save(gold, os.path.join(GOLD, name + ".pt"))
     print(name, "loss", float(out.loss), "prob", float(prob_loss), "img", float(img_loss))
+
+
+def gen_tvnet_span(name, c):
+    """Span variant TVNetSAModel (models/bert_model.py:192-414), eval mode, with prefix and probe."""
+    ocfg = ocfg_for(c["kind"])
+    params = S.init_params(ocfg, seed=c["param_seed"], ln_jitter=0.05, with_span=True)
+    batch = S.make_span_batch(c["B"], c["L"], M=c["M"], vocab=ocfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    args = ref_shim.make_args(vao=False)
+    model = ref_shim.build_reference_tvnet2(hf_config(ocfg), args, list(range(10)), cls_name="TVNetSAModel")
+    missing = model.load_state_dict({k: v for k, v in params.items() if k in model.state_dict()}, strict=False)
+    assert all("position_ids" in k or "token_type_ids" in k for k in missing.missing_keys), missing
+    model.eval()
+    out, prob_loss, tot_loss = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
+                                     token_type_ids=batch["token_type_ids"],
+                                     start_positions=batch["start_positions"], end_positions=batch["end_positions"],
+                                     span_starts=batch["span_starts"], span_ends=batch["span_ends"],
+                                     polarity_labels=batch["polarity_labels"], label_masks=batch["label_masks"],
+                                     images=batch["images"], aux_imgs=batch["aux_imgs"])
+    out.loss.backward()
+    gold = {"case": c, "loss": out.loss.detach(), "prob_loss": prob_loss.detach(), "tot_loss": tot_loss.detach(),
+            "logits": out.logits.detach().clone(),
+            "grad_fp": grad_fingerprint([(k, v.grad) for k, v in model.named_parameters()])}
+    torch.save(gold, os.path.join(GOLD, name + ".pt"))
+    print(name, "loss", float(out.loss), "prob", float(prob_loss), "tot", float(tot_loss))
 
 
 def gen_encoder(name, c):
@@ -190,6 +215,7 @@ def main():
     gen_encoder("encoder_roberta_p36", CASES["encoder_roberta_p36"])
     gen_encoder("encoder_bert", CASES["encoder_bert"])
     gen_tvnet2("tvnet2_roberta", CASES["tvnet2_roberta"])
+    gen_tvnet_span("tvnet_span_roberta", CASES["tvnet_span_roberta"])
 
 
 if __name__ == "__main__":

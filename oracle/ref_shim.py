@@ -174,8 +174,9 @@ class FeatureStub(nn.Module):
         return main, [self._split(aux[i]) for i in range(aux.shape[0])]
 
 
-def build_reference_tvnet2(config, args, label_list, probe_proj=None, seed=0):
-    """Construct the reference TVNetSAModel2 offline (random-init encoder from `config`)."""
+def build_reference_tvnet2(config, args, label_list, probe_proj=None, seed=0, cls_name="TVNetSAModel2"):
+    """Construct the reference TVNetSAModel2 (or the span variant TVNetSAModel) offline (random-init encoder from
+    `config`)."""
     R = load_reference()
     bm = R.bert_model
     torch.manual_seed(seed)
@@ -205,7 +206,7 @@ def build_reference_tvnet2(config, args, label_list, probe_proj=None, seed=0):
     torch.load = fake_load
     # probe checkpoint was pickled with module path 'probe_trainModel' (on sys.path via probes/)
     try:
-        model = bm.TVNetSAModel2(label_list, None, args)
+        model = getattr(bm, cls_name)(label_list, None, args)
     finally:
         enc_cls.from_pretrained = orig_from_pretrained
         bm.ImageModel = orig_image_model

@@ -233,3 +233,94 @@ def test_cpu_tensors_fail_loudly():
     m = RobertaModel.from_config(hf_config(cfg))
     with pytest.raises(lib.MtvafError):
         m(input_ids=torch.zeros(1, 8, dtype=torch.long), attention_mask=torch.ones(1, 8))
+
+
+# ------------------------------------------------------------------ span variant TVNetSAModel
+def build_tvnet_span(cfg, params, dtype, **akw):
+    from mtvaf_b200.modules import TVNetSAModel, FeatureStub
+    args = make_args(compute_dtype=dtype, vao=False, num_epochs=30, gcn_layer_number=0, num_layers=0, **akw)
+    m = TVNetSAModel(list(range(10)), None, args, config=hf_config(cfg), image_model=FeatureStub())
+    own = m.state_dict()
+    missing = m.load_state_dict({k: v for k, v in params.items() if k in own}, strict=False)
+    assert all("position_ids" in k for k in missing.missing_keys), missing.missing_keys
+    return m.to(DEV)
+
+
+def _span_kwargs(batch):
+    keys = ("input_ids", "attention_mask", "token_type_ids", "start_positions", "end_positions", "span_starts",
+            "span_ends", "polarity_labels", "label_masks", "images", "aux_imgs")
+    return {k: batch[k].to(DEV) for k in keys}
+
+
+def test_tvnet_span_fp32_matches_reference_golden(golden_dir):
+    g = _gold(golden_dir, "tvnet_span_roberta")
+    c = CASES["tvnet_span_roberta"]
+    cfg = ocfg_for(c["kind"])
+    params = S.init_params(cfg, seed=c["param_seed"], ln_jitter=0.05, with_span=True)
+    batch = S.make_span_batch(c["B"], c["L"], M=c["M"], vocab=cfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    m = build_tvnet_span(cfg, params, "fp32")
+    m.eval()
+    out, prob_loss, tot_loss = m(**_span_kwargs(batch))
+    assert rel(out.loss, g["loss"]) < 1e-4
+    assert rel(tot_loss, g["tot_loss"]) < 1e-4
+    assert rel(prob_loss, g["prob_loss"]) < 1e-4
+    assert rel(out.logits, g["logits"]) < 1e-4
+    out.loss.backward()
+    fp = grad_fingerprint([(k, v.grad) for k, v in m.named_parameters() if v.grad is not None])
+    check_fp(fp, g["grad_fp"], 2e-3)
+    for k in ("dense.weight", "unary_affine.weight", "binary_affine.weight", "classifier.weight",
+              "bert.encoder.layer.0.attention.self.query.weight", "encoder_conv.0.weight"):
+        assert k in fp, k
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_tvnet_span_matches_oracle(dtype, tol):
+    """Ragged spans (widths 1..4, padded (0,0) spans), B=5, L=48, M=8, prefix + probe, against the oracle."""
+    cfg = O.EncoderCfg.roberta_base(vocab_size=1500)
+    params = S.init_params(cfg, seed=17, ln_jitter=0.05, with_span=True)
+    batch = S.make_span_batch(5, 48, M=8, vocab=1500, shape="twitter2017", seed=18)
+    p = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    o = O.tvnet_forward(p, cfg, batch, beta=0.5, num_epochs=30)
+    o["loss"].backward()
+    m = build_tvnet_span(cfg, params, dtype)
+    m.eval()
+    out, prob_loss, tot_loss = m(**_span_kwargs(batch))
+    assert rel(out.loss, o["loss"]) < tol
+    assert rel(tot_loss, o["tot_loss"]) < tol
+    assert rel(out.logits, o["logits"]) < (tol if dtype == "fp32" else 5e-2)
+    out.loss.backward()
+    gtol = 5e-3 if dtype == "fp32" else 8e-2
+    for k, prm in m.named_parameters():
+        if k not in p or p[k].grad is None or prm.grad is None:
+            continue
+        ref = p[k].grad
+        if float(ref.norm()) < 1e-6:
+            continue
+        err = float((prm.grad.cpu() - ref).norm() / ref.norm())
+        lim = gtol if (dtype == "fp32" or not k.startswith("projectors.")) else 0.3
+        assert err < lim, (k, err)
+    # inference entry points used by the trainer (modules/train.py:341,362-380)
+    with torch.no_grad():
+        kv = m.get_visual_prompt(batch["images"].to(DEV), batch["aux_imgs"].to(DEV))
+        B = batch["input_ids"].shape[0]
+        pm = torch.cat([torch.ones(B, 16, device=DEV), batch["attention_mask"].to(DEV).float()], 1)
+        s_log, e_log, seq, pl = m.extraction(pm, batch["input_ids"].to(DEV), kv, batch["token_type_ids"].to(DEV))
+        logits, ac = m.classification(batch["span_starts"].to(DEV), batch["span_ends"].to(DEV), seq,
+                                      batch["attention_mask"].to(DEV))
+    assert rel(s_log, o["start_logits"]) < (tol if dtype == "fp32" else 5e-2)
+    assert rel(logits, o["logits"]) < (tol if dtype == "fp32" else 5e-2)
+
+
+def test_tvnet_span_training_mode_runs():
+    cfg = O.EncoderCfg.roberta_base(vocab_size=800)
+    params = S.init_params(cfg, seed=19, with_span=True)
+    batch = S.make_span_batch(3, 40, M=6, vocab=800, seed=20)
+    m = build_tvnet_span(cfg, params, "bf16")
+    m.train()
+    out, _, _ = m(**_span_kwargs(batch))
+    assert torch.isfinite(out.loss)
+    out.loss.backward()
+    for k, prm in m.named_parameters():
+        if "pooler" in k or "image_model" in k or k.startswith("fc."):
+            continue
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), k

@@ -621,3 +621,55 @@ def test_colsum(ops, dtype, M, N, ld):
     ops.colsum(x, db, n_valid=N)
     ref = x[:, :N].float().sum(0) + 0.5
     assert rel_err(db, ref) < 1e-4
+
+
+def test_span_heads_kernels(ops):
+    """distant CE, mean CE and the ragged span pooling (fwd + bwd) against the oracle's torch restatement."""
+    g = torch.Generator().manual_seed(3)
+    B, Lq, M, H = 4, 24, 5, 768
+    lens = torch.tensor([24, 9, 17, 3])
+    mask = (torch.arange(Lq)[None] < lens[:, None]).long()
+    seq = torch.randn(B, Lq, H, generator=g).requires_grad_()
+    starts = torch.tensor([[1, 5, 0, 0, 20], [2, 0, 0, 0, 0], [3, 10, 16, 0, 0], [1, 0, 0, 0, 0]])
+    ends = torch.tensor([[3, 5, 0, 0, 23], [8, 0, 0, 0, 0], [4, 12, 16, 0, 0], [2, 0, 0, 0, 0]])
+    w = (torch.randn(1, H, generator=g) * 0.05).requires_grad_()
+    b = torch.tensor([0.1], requires_grad=True)
+    emb, smask = O.span_representation(starts, ends, seq, mask)
+    score = F.linear(emb, w, b).squeeze(-1)
+    ref = O.self_att_representation(emb, score, smask)
+    dpool = torch.randn(ref.shape, generator=g)
+    ref.backward(dpool)
+    ws = ops.span_offsets(mask.to(DEV))
+    assert ws[:B].tolist() == lens.tolist() and int(ws[2 * B]) == int(lens.sum())
+    sd = seq.detach().reshape(B * Lq, H).to(DEV).contiguous()
+    pooled = ops.span_pool_fwd(sd, ws, starts.to(DEV), ends.to(DEV), w.detach().view(-1).to(DEV), b.detach().to(DEV),
+                               B, Lq)
+    assert rel_err(pooled, ref) < 1e-5
+    d_seq = torch.zeros(B * Lq, H, device=DEV)
+    d_w, d_b = torch.zeros(H, device=DEV), torch.zeros(1, device=DEV)
+    ops.span_pool_bwd(dpool.to(DEV), sd, ws, starts.to(DEV), ends.to(DEV), w.detach().view(-1).to(DEV),
+                      b.detach().to(DEV), B, Lq, d_seq, d_w, d_b)
+    assert rel_err(d_seq, seq.grad.reshape(B * Lq, H)) < 1e-4
+    assert rel_err(d_w, w.grad.view(-1)) < 1e-4
+    assert abs(float(d_b) - float(b.grad)) < 1e-4 * (1 + abs(float(b.grad)))
+    # distant cross-entropy on the two columns of a [T, 2] matrix
+    ae = torch.randn(B * Lq, 2, generator=g).requires_grad_()
+    pos = torch.zeros(B, Lq, dtype=torch.long)
+    pos[0, 3] = pos[0, 7] = pos[1, 2] = pos[2, 5] = pos[3, 1] = 1
+    l0 = O.distant_cross_entropy(ae.view(B, Lq, 2)[..., 0], pos)
+    l1 = O.distant_cross_entropy(ae.view(B, Lq, 2)[..., 1], pos)
+    ((l0 + l1) / 2).backward()
+    loss = torch.zeros(1, device=DEV)
+    d_ae = torch.empty(B * Lq, 2, device=DEV)
+    ops.distant_ce(ae.detach().to(DEV), 0, pos.to(DEV), 0.5, loss, d_ae)
+    ops.distant_ce(ae.detach().to(DEV), 1, pos.to(DEV), 0.5, loss, d_ae)
+    assert abs(float(loss) - float((l0 + l1) / 2)) < 1e-5
+    assert rel_err(d_ae, ae.grad) < 1e-5
+    # mean cross-entropy
+    lg = torch.randn(37, 4, generator=g).requires_grad_()
+    y = torch.randint(0, 4, (37,), generator=g)
+    F.cross_entropy(lg, y).backward()
+    loss = torch.zeros(1, device=DEV)
+    d = ops.ce_mean(lg.detach().to(DEV), y.to(DEV), 1.0, loss, True)
+    assert abs(float(loss) - float(F.cross_entropy(lg, y))) < 1e-5
+    assert rel_err(d, lg.grad) < 1e-5

@@ -106,6 +106,26 @@ def test_tvnet2_matches_reference_golden(golden_dir):
     _check_fp(fp, g["grad_fp"], 5e-4)
 
 
+def test_tvnet_span_matches_reference_golden(golden_dir):
+    """Span variant TVNetSAModel: oracle restatement vs the unmodified reference."""
+    g = _load(golden_dir, "tvnet_span_roberta")
+    c = CASES["tvnet_span_roberta"]
+    cfg = ocfg_for(c["kind"])
+    params = S.init_params(cfg, seed=c["param_seed"], ln_jitter=0.05, with_span=True)
+    params = {k: v.requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    batch = S.make_span_batch(c["B"], c["L"], M=c["M"], vocab=cfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    o = O.tvnet_forward(params, cfg, batch, beta=0.5, num_epochs=30)
+    _close(o["loss"], g["loss"], rtol=1e-5, atol=1e-5)
+    _close(o["tot_loss"], g["tot_loss"], rtol=1e-5, atol=1e-5)
+    _close(o["prob_loss"], g["prob_loss"], rtol=1e-5, atol=1e-2)
+    _close(o["logits"], g["logits"], rtol=1e-4, atol=1e-5)
+    o["loss"].backward()
+    fp = grad_fingerprint([(k, v.grad) for k, v in params.items() if k in g["grad_fp"]])
+    _check_fp(fp, {k: v for k, v in g["grad_fp"].items() if k in fp}, 5e-4)
+    for k in ("dense.weight", "unary_affine.weight", "binary_affine.weight", "classifier.weight"):
+        assert k in fp and g["grad_fp"][k] is not None, k
+
+
 def test_crf_against_bruteforce():
     """pytorch-crf is absent (parity unpinned): check the restated forward algorithm / Viterbi
     against explicit enumeration of all tag paths on a tiny problem."""
