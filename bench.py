@@ -266,8 +266,9 @@ def main():
     barrier()
     ops.GEMM_EVENT_SINK = None
     eager_ms = p0.elapsed_time(p1) / n_prof
-    g_fl = sum(f for (_, _, f) in gemm_events)
-    g_ms = sum(a.elapsed_time(b) for (a, b, _) in gemm_events)
+    g_fl = sum(e[2] for e in gemm_events)
+    gemm_alg_bytes = sum(e[3] for e in gemm_events)      # operands + results (+ fused aux / second output) once each
+    g_ms = sum(e[0].elapsed_time(e[1]) for e in gemm_events)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -275,6 +276,16 @@ def main():
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    # DRAM bytes per GEMM launch: taken from the committed ncu capture of the SAME eager step (never measured under a
+    # profiler here); null when the capture is for another batch size
+    traffic, traffic_src = None, None
+    try:
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if "gemm_traffic" in f and f.endswith(".json"))
+        if cands and B == 256 and args.dtype == "bf16":
+            tj = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
+            traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/" + cands[-1]
+    except Exception:
+        pass
     gemm_ms_per_step = g_ms / n_prof
 
     # ---- timed region 2: end to end through the public API with HOST buffers (pinned) -> `e2e`
@@ -340,7 +351,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05)", "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": gemm_alg_bytes / max(1, len(gemm_events)),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback",
                          "gemm_launches_per_step": len(gemm_events) // n_prof,
                          "gemm_ms_per_step": gemm_ms_per_step,

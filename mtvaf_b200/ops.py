@@ -34,7 +34,7 @@ def _stream():
 
 # the library counts its own kernel launches (mtvaf_launch_count); the bench reports the count of OUR launches
 _launch_base = 0
-GEMM_EVENT_SINK = None      # bench.py: list receiving (start_event, end_event, flops) per tcgen05 GEMM launch
+GEMM_EVENT_SINK = None      # bench.py: list receiving (start_event, end_event, flops, algorithmic bytes) per tcgen05 GEMM launch
 
 
 def reset_launch_count():
@@ -99,7 +99,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
             splits, _stream())
     if sink is not None:
         e1.record()
-        sink.append((e0, e1, 2.0 * M * N * K))
+        nbytes = 2 * (M * K + N * K) + (M * N * out.element_size() if out is not None else 0)
+        nbytes += (M * N * 2 if aux is not None else 0) + (M * N * 2 if out2 is not None else 0)
+        sink.append((e0, e1, 2.0 * M * N * K, nbytes))
     _check(rc, "mtvaf_gemm")
     return out
 

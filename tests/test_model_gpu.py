@@ -266,7 +266,7 @@ def test_tvnet_span_fp32_matches_reference_golden(golden_dir):
     assert rel(prob_loss, g["prob_loss"]) < 1e-4
     assert rel(out.logits, g["logits"]) < 1e-4
     out.loss.backward()
-    fp = grad_fingerprint([(k, v.grad) for k, v in m.named_parameters() if v.grad is not None])
+    fp = grad_fingerprint([(k, v.grad.cpu()) for k, v in m.named_parameters() if v.grad is not None])
     check_fp(fp, g["grad_fp"], 2e-3)
     for k in ("dense.weight", "unary_affine.weight", "binary_affine.weight", "classifier.weight",
               "bert.encoder.layer.0.attention.self.query.weight", "encoder_conv.0.weight"):

@@ -37,6 +37,7 @@ def main():
         rows.append((d["Kernel Name"], us))
     agg = OrderedDict()
     for name, us in rows:
+        name = name.replace("<unnamed>::", "")
         name = re.sub(r"<.*", "", name)
         name = re.sub(r"\(.*", "", name)
         name = name.replace("void ", "")
