@@ -163,12 +163,34 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
+    layer_ctas = int(os.environ.get("MTVAF_NCCL_CTAS", 4))
+    tail_ctas = int(os.environ.get("MTVAF_TAIL_CTAS", 32))
+    reserve = int(os.environ.get("MTVAF_SM_RESERVE", 2 * layer_ctas))
+    tail_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # The gradient all-reduce has the whole backward pass to hide behind (500 MB per ~15 ms): a few CTAs are
-        # plenty, and every SM NCCL does not occupy stays with the persistent tcgen05 kernels (one CTA per SM).
-        os.environ.setdefault("NCCL_MAX_CTAS", "4")
-        dist.init_process_group("nccl", device_id=dev)
+        # Two communicators.  The per-layer gradient all-reduces have the rest of backward to hide behind (340 MB per
+        # ~15 ms): `layer_ctas` CTAs are plenty, and the persistent tcgen05 kernels size their grids around them
+        # (GradSync reserve_sms).  The tail (embedding tables, fusion MLP: final only when backward ends) is exposed,
+        # so it goes out on a wide communicator while AdamW updates the layers.
+        def nccl_opts(max_ctas):
+            try:
+                o = dist.ProcessGroupNCCL.Options()
+                o.config.max_ctas = max_ctas
+                o.config.min_ctas = 1
+                return o
+            except Exception:
+                return None
+        o1 = nccl_opts(layer_ctas)
+        if o1 is None:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(layer_ctas))
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group("nccl", device_id=dev, pg_options=o1)
+            try:
+                tail_group = dist.new_group(pg_options=nccl_opts(tail_ctas))
+            except Exception:
+                tail_group = None
 
     from oracle.make_golden import hf_config          # config helper only (no oracle arithmetic)
     from oracle import mtvaf_oracle as O
@@ -186,7 +208,7 @@ def main():
     eng.base_seed = 0x5EED + rank                        # different dropout streams per rank
     total_steps = args.warmup + 2 * args.steps + 8
     opt = FlatAdamW(eng, lr=LR, warmup_steps=max(1, total_steps // 100), total_steps=total_steps * 50)
-    sync = GradSync(eng) if world > 1 else None
+    sync = GradSync(eng, tail_group=tail_group, optimizer=opt, reserve_sms=reserve) if world > 1 else None
 
     # distinct synthetic batches per rank (DistributedSampler-style disjoint shards), pinned on the host
     n_host = 4
@@ -203,9 +225,9 @@ def main():
     def step(batch):
         out, prob, img = model(**batch)
         out.loss.backward()
-        if sync is not None:
-            sync.finish()
-        opt.step(zero_grad=True)          # AdamW + gradient clear in one pass over the flat buffers
+        # AdamW + gradient clear in one pass over the flat buffers; data parallel: the tail all-reduce is launched
+        # first and the encoder layers (reduced during backward) are updated beneath it
+        opt.step(zero_grad=True, sync=sync)
         return out.loss
 
     def barrier():
@@ -342,6 +364,10 @@ def main():
                                    "configs[1])",
                        "per_gpu_batch": B, "global_batch": B * world, "seq_len": L_TEXT, "prefix_rows": 16,
                        "parallelism": "dp%d" % world,
+                       "dp": None if world == 1 else {"layer_allreduce_ctas": layer_ctas, "tail_allreduce_ctas": tail_ctas
+                                                      if tail_group is not None else layer_ctas,
+                                                      "sm_reserve_during_backward": reserve,
+                                                      "reduced": "optimizer-owned ranges only"},
                        "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "launch": "eager (one Python/ctypes call per kernel)" if graphed is None else
                                  "whole step (fwd+bwd+all-reduce+AdamW) replayed from one CUDA graph",

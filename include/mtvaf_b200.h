@@ -80,6 +80,12 @@ int mtvaf_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, i
 /* 0 (default) = CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) whenever M >= 256, single-CTA
  * 128 x 256 tiles otherwise; 1 = single-CTA kernel only (A/B testing). */
 int mtvaf_set_gemm_impl(int impl);
+/* Leave `n_sms` SMs (rounded down to whole TPCs) out of the grids of the persistent kernels (GEMM, attention,
+ * LayerNorm ...).  Data-parallel training sets this to the CTA budget of the gradient all-reduce while backward
+ * runs: persistent kernels with a static tile schedule would otherwise wait for the SMs the collective holds and
+ * run their share of tiles after everyone else.  0 (default) = use every SM.  Replaces nothing in the reference
+ * (modules/parallel.py never overlaps communication). */
+int mtvaf_set_sm_reserve(int n_sms);
 /* fp32 operands, fp32 FFMA (parity mode; also used for skinny heads such as fc 768->11). */
 int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, const MtvafEpilogue* epi, int splits, void* stream);

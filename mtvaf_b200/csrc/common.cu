@@ -23,8 +23,10 @@ void set_step_source(const unsigned long long* p) { g_step_source = p; }
 static std::atomic<unsigned long long> g_launches{0};   // statistics only: kernels launched by this library
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-int sm_count() {
-  static int n = 0;   // read-only device-properties cache (the only global state of the library)
+static std::atomic<int> g_sm_reserve{0};   // see mtvaf_set_sm_reserve
+
+static int sm_count_device() {
+  static int n = 0;   // read-only device-properties cache
   if (n == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -33,11 +35,25 @@ int sm_count() {
   return n;
 }
 
+// SMs the persistent kernels size their grids for: all of them minus the reserve left to a concurrent collective
+int sm_count() {
+  const int n = sm_count_device() - g_sm_reserve.load(std::memory_order_relaxed);
+  return n < 2 ? 2 : n;
+}
+
 }  // namespace mtvaf
 
 extern "C" int mtvaf_abi_version(void) { return MTVAF_ABI_VERSION; }
 extern "C" int mtvaf_set_step_source(const uint64_t* dev_step) {
   mtvaf::set_step_source(reinterpret_cast<const unsigned long long*>(dev_step));
+  return 0;
+}
+extern "C" int mtvaf_set_sm_reserve(int n_sms) {
+  if (n_sms < 0 || n_sms >= mtvaf::sm_count_device() - 1) {
+    mtvaf::set_last_error("mtvaf_set_sm_reserve: %d out of range", n_sms);
+    return -1;
+  }
+  mtvaf::g_sm_reserve.store(n_sms & ~1, std::memory_order_relaxed);   // whole TPCs (CTA pairs)
   return 0;
 }
 extern "C" uint64_t mtvaf_launch_count(void) { return mtvaf::g_launches.load(std::memory_order_relaxed); }

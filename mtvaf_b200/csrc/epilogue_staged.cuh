@@ -45,40 +45,41 @@ __device__ __forceinline__ uint32_t dropout_mask32(unsigned long long seed, unsi
   return keep;
 }
 
+// bias of 32 consecutive columns into registers (issued BEFORE the TMEM wait so the latency hides behind it);
+// all lanes read the same addresses (one broadcast transaction per load)
+__device__ __forceinline__ void epi_load_bias32(const EpiArgs& ep, int col0, int N, bool full, float (&b)[32]) {
+  if (ep.bias == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
+  } else if (full) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + g * 4));
+      b[g * 4] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = (col0 + j < N) ? __ldg(ep.bias + col0 + j) : 0.f;
+  }
+}
+
 // math of one 32-column chunk of one row: acc (TMEM registers) -> packed bf16 pairs.
-// aux4: the thread's 4 x 16-byte pieces (32 bf16) of the auxiliary operand, already in registers.
-// FULL: all 32 columns are < N (no per-element guards on the bias loads).
-template <int MODE, bool FULL>
-__device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t (&r)[32], const uint4 (&aux4)[4],
-                                              int row, int col0, int N, uint32_t (&outp)[16], uint32_t (&prep)[16]) {
+// bias: the 32 bias values (zeros when there is none); aux4: the thread's 4 x 16-byte pieces (32 bf16) of the
+// auxiliary operand, already in registers.
+template <int MODE>
+__device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t (&r)[32], const float (&bias)[32],
+                                              const uint4 (&aux4)[4], int row, int col0, int N, uint32_t (&outp)[16],
+                                              uint32_t (&prep)[16]) {
   constexpr bool needs_aux = StagedEpi<MODE>::kAux;
   uint32_t keep = 0xFFFFFFFFu;
   if (MODE == MTVAF_EPI_RESID && ep.drop_threshold)
     keep = dropout_mask32(ep.seed, (unsigned long long)row * (unsigned long long)N + col0, ep.drop_threshold);
-  const bool has_bias = ep.bias != nullptr;
   const float alpha = ep.alpha;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float v[8], a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-    if (alpha != 1.f) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= alpha;
-    }
-    if (has_bias) {
-      const int c = col0 + g * 8;
-      if (FULL) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + 4));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c + j < N) v[j] += __ldg(ep.bias + c + j);
-      }
-    }
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), alpha, bias[g * 8 + j]);
     if (needs_aux) {
       const float2 a0 = unpack_bf16x2(aux4[g].x), a1 = unpack_bf16x2(aux4[g].y), a2 = unpack_bf16x2(aux4[g].z),
                    a3 = unpack_bf16x2(aux4[g].w);

@@ -38,6 +38,21 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Signal without a memory fence.  For "this TMEM accumulator has been read": the reads are already complete
+// (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; nothing written to memory has to be visible
+// to the MMA issuer.  The .release.cluster form costs MEMBAR.ALL.GPU + ERRBAR per arrival -- 25 % of all warp
+// samples of the fused-epilogue GEMMs (profiles/r1_ncu_hot_v7.md).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 // TMA load into THIS CTA's smem, completion bytes signalled on an mbarrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
                                                 int c0, int c1) {
@@ -268,32 +283,47 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int col0 = w.tn * BN + half * (BN / 2) + j * 64;
           if (col0 >= N) continue;                   // warp-uniform
           const uint32_t ab = used & 1;
+          const bool full = col0 + 64 <= N;
+          const uint32_t out_a = smem_u32(out_box), aux_a = smem_u32(aux_box) + ab * kEpiBoxBytes;
+          // software pipeline over the two 32-column halves of the box: the TMEM load of half 1 and the bias loads
+          // are in flight while half 0 is computed; the staging box is only claimed (previous TMA store done
+          // READING it) right before the first write, i.e. after a whole half of math
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_addr + j * 64, r0);
+          float bias0[32], bias1[32];
+          epi_load_bias32(ep, col0, N, full, bias0);
           if (SE::kAux) mbar_wait(&my_bar[ab], (used >> 1) & 1);
-          // the previous TMA store(s) must have finished READING the staging box(es) before we overwrite them
+          uint4 aux4[4];
+          if (SE::kAux) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) aux4[g] = ld_shared_v4(aux_a + box_piece_off(lane, g));
+          }
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(t_addr + j * 64 + 32, r1);
+          epi_load_bias32(ep, col0 + 32, N, full, bias1);
+          uint32_t o[16], p[16];
+          epi_compute32<EPI>(ep, r0, bias0, aux4, row, col0, N, o, p);
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_addr + j * 64 + sub * 32, r);
-            uint4 aux4[4];
-            if (SE::kAux) {
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = box_piece_off(lane, g);
+            st_shared_v4(out_a + off, o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+            if (EPI == MTVAF_EPI_GELU)
+              st_shared_v4(out_a + kEpiBoxBytes + off, p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
+          }
+          if (SE::kAux) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g)
-                aux4[g] = *reinterpret_cast<const uint4*>(aux_box + ab * kEpiBoxBytes + box_piece_off(lane, sub * 4 + g));
-            }
-            tmem_ld_wait();
-            uint32_t o[16], p[16];
-            if (col0 + 64 <= N) epi_compute32<EPI, true>(ep, r, aux4, row, col0 + sub * 32, N, o, p);
-            else epi_compute32<EPI, false>(ep, r, aux4, row, col0 + sub * 32, N, o, p);
+            for (int g = 0; g < 4; ++g) aux4[g] = ld_shared_v4(aux_a + box_piece_off(lane, 4 + g));
+          }
+          tmem_ld_wait();
+          epi_compute32<EPI>(ep, r1, bias1, aux4, row, col0 + 32, N, o, p);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t off = box_piece_off(lane, sub * 4 + g);
-              *reinterpret_cast<uint4*>(out_box + off) = make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
-              if (EPI == MTVAF_EPI_GELU)
-                *reinterpret_cast<uint4*>(out_box + kEpiBoxBytes + off) =
-                    make_uint4(p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
-            }
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = box_piece_off(lane, 4 + g);
+            st_shared_v4(out_a + off, o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+            if (EPI == MTVAF_EPI_GELU)
+              st_shared_v4(out_a + kEpiBoxBytes + off, p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
           }
           fence_proxy_async_smem();                  // staging writes (and aux reads) ordered before the TMA ops
           __syncwarp();
@@ -302,10 +332,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (EPI == MTVAF_EPI_GELU && ep.out2) tma_store_2d(&tmOut2, out_box + kEpiBoxBytes, col0, row0);
             tma_store_commit();
             if (SE::kAux) {                          // refill the aux box just consumed with the box two ahead
-              int r0, c0;
-              if (pf_next(r0, c0)) {
+              int r0n, c0n;
+              if (pf_next(r0n, c0n)) {
                 mbar_arrive_expect_tx(&my_bar[ab], kEpiBoxBytes);
-                tma_load_2d(aux_box + ab * kEpiBoxBytes, &tmAux, &my_bar[ab], c0, r0);
+                tma_load_2d(aux_box + ab * kEpiBoxBytes, &tmAux, &my_bar[ab], c0n, r0n);
               }
             }
           }
@@ -313,7 +343,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) tma_store_wait<0>();            // all output bytes written before the CTA retires
@@ -340,7 +370,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         epilogue_row_finish<EPI>(ep, row, M, rowacc);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

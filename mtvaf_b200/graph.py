@@ -58,9 +58,8 @@ class GraphedTrainStep:
         out = self.model(**self.static)
         loss = out[0].loss if isinstance(out, tuple) else out.loss
         loss.backward()
-        if self.sync is not None:
-            self.sync.finish()
-        self.opt.step(zero_grad=True)
+        # data parallel: the tail all-reduce is launched here and AdamW of the encoder layers runs beneath it
+        self.opt.step(zero_grad=True, sync=self.sync)
         return loss.detach()
 
     # ------------------------------------------------------------------ inputs

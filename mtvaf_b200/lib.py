@@ -35,6 +35,7 @@ SIGNATURES = {
     "mtvaf_device_info": [_vp, _vp, _vp],
     "mtvaf_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
     "mtvaf_set_gemm_impl": [_i],
+    "mtvaf_set_sm_reserve": [_i],
     "mtvaf_gemm_f32": [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _vp],
     "mtvaf_skinny_linear_f32": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp],
     "mtvaf_skinny_linear_dgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _u64, _vp, _i64, _i, _vp, _vp],

@@ -116,6 +116,16 @@ def set_gemm_impl(impl: str):
 _GEMM_PAIR = True
 
 
+_SM_RESERVE = 0
+
+
+def set_sm_reserve(n_sms: int):
+    """SMs the persistent kernels leave to a concurrent collective (whole TPCs; 0 = none)."""
+    global _SM_RESERVE
+    _check(_raw.mtvaf_set_sm_reserve(int(n_sms)), "set_sm_reserve")
+    _SM_RESERVE = int(n_sms) & ~1
+
+
 def linear_fwd(x, w, bias=None, **kw):
     """y = x w^T + b  (x [M,K], w [N,K])"""
     return gemm(x, w, M=x.shape[0], N=w.shape[0], K=x.shape[1], bias=bias, **kw)
@@ -128,9 +138,10 @@ def linear_dgrad(dy, w, **kw):
 
 def wgrad_splits(m_out: int, n_out: int, k: int, bf16: bool) -> int:
     bm, bn = (128, 256 if n_out > 128 else 128) if bf16 else (128, 128)
-    slots = 148 * (1 if bf16 else 2)          # persistent CTAs (bf16) / resident blocks (fp32)
+    sms = 148 - _SM_RESERVE
+    slots = sms * (1 if bf16 else 2)          # persistent CTAs (bf16) / resident blocks (fp32)
     if bf16 and _GEMM_PAIR and m_out >= 256:
-        bm, slots = 256, 74                   # CTA-pair kernel: 256-row tiles, one cluster per TPC
+        bm, slots = 256, sms // 2             # CTA-pair kernel: 256-row tiles, one cluster per TPC
     tiles = ((m_out + bm - 1) // bm) * ((n_out + bn - 1) // bn)
     kb = max(1, k // (64 if bf16 else 16))
     best, best_score = 1, -1.0

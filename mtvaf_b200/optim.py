@@ -77,11 +77,18 @@ class FlatAdamW:
             return s / max(1.0, float(self.warmup_steps))
         return max(0.0, (self.total_steps - s) / max(1.0, float(self.total_steps - self.warmup_steps)))
 
-    def step(self, grad_scale: float = 1.0, zero_grad: bool = False):
+    def step(self, grad_scale: float = 1.0, zero_grad: bool = False, sync: Optional["GradSync"] = None):
         """One AdamW update of every range.  zero_grad=True clears the whole flat gradient buffer in the same
         pass (the update kernels clear the ranges they own, one memset per gap of never-updated parameters),
-        replacing `optimizer.zero_grad()` / `model.zero_grad()` and its one-fill-per-parameter launches."""
+        replacing `optimizer.zero_grad()` / `model.zero_grad()` and its one-fill-per-parameter launches.
+        With `sync` (data parallel) the tail all-reduce is launched first and the encoder-layer ranges -- already
+        reduced during backward -- are updated while it is in flight; the tail ranges follow once it lands."""
         f = self.engine.flat
+        tail_lo = None
+        if sync is not None and sync.world > 1:
+            sync.launch_tail()
+            sync.wait_layers()
+            tail_lo = f.layer_ranges[-1][1] if f.layer_ranges else 0
         scale = self.lr_scale()
         self.t += 1
         if self.dyn is not None:
@@ -89,12 +96,18 @@ class FlatAdamW:
             ops.adam_dyn_advance(self.dyn, self.betas[0], self.betas[1], self.warmup_steps, self.total_steps)
             scale = 1.0
         bf = self.engine.bf16 and f.Wb is not None
+        pending = tail_lo is not None
         for a, b, lr, wd in self.ranges:
+            if pending and (b > tail_lo or a < (f.layer_ranges[0][0] if f.layer_ranges else 0)):
+                sync.wait_tail()            # ranges are sorted: everything from here on is tail
+                pending = False
             shadow = None
             if bf and b <= f.cast_end:
                 shadow = f.Wb[a:b]
             ops.adamw_step(f.W[a:b], f.G[a:b], self.m[a:b], self.v[a:b], lr * scale, self.betas[0], self.betas[1],
                            self.eps, wd, self.t, grad_scale, shadow, zero_grad, self.dyn)
+        if pending:
+            sync.wait_tail()
         if zero_grad:
             for a, b in self._gaps():
                 f.G[a:b].zero_()
@@ -118,52 +131,121 @@ class FlatAdamW:
 
 
 class GradSync:
-    """NCCL gradient all-reduce (average) of the flat gradient buffer, per encoder layer, overlapped
-    with backward.  Usage: sync = GradSync(engine); loss.backward(); sync.finish(); optimizer.step()."""
+    """NCCL gradient all-reduce (average) of the flat gradient buffer, overlapped with backward.
 
-    def __init__(self, engine: Engine, group=None):
+    * per encoder layer, issued from inside backward on a side stream the moment layer i's gradients are final
+      (`Engine.layer_grad_hook`) on the process group `group` -- bench.py caps that communicator at a few CTAs
+      because these transfers have the rest of backward to hide behind;
+    * the TAIL (heads, fusion MLP, embedding tables: final only when backward ends, so nothing hides it) goes out
+      on `tail_group` (a second communicator WITHOUT the CTA cap when bench.py provides one), and
+      `FlatAdamW.step(sync=...)` updates the already-reduced encoder layers while the tail is in flight;
+    * `reserve_sms`: while layer all-reduces are resident the persistent kernels (static tile schedules) size their
+      grids for `SMs - reserve_sms`, so none of their CTAs queues behind the SMs the collective holds;
+    * with `optimizer=` only the ranges that optimizer updates are reduced: gradients of parameters the reference
+      never steps (ANP heads, gate projectors, probe -- modules/train.py:894-926; 51 M of them) stay rank-local.
+
+    Usage: sync = GradSync(engine, optimizer=opt); loss.backward(); opt.step(zero_grad=True, sync=sync)
+       or: sync = GradSync(engine); loss.backward(); sync.finish(); optimizer.step()"""
+
+    def __init__(self, engine: Engine, group=None, tail_group=None, optimizer: Optional["FlatAdamW"] = None,
+                 reserve_sms: int = 0):
         import torch.distributed as dist
         self.dist = dist
         self.engine = engine
         self.group = group
+        self.tail_group = tail_group if tail_group is not None else group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.works = []
+        self.works = []            # layer all-reduces in flight
+        self.tail_works = []
         self.done_layers = set()
         self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.tail_side = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.owned = None if optimizer is None else sorted((a, b) for a, b, _, _ in optimizer.ranges)
+        # SMs the persistent kernels leave alone while layer all-reduces are resident (mtvaf_set_sm_reserve): set
+        # when the first layer hook fires, cleared in wait_layers()
+        self.reserve_sms = reserve_sms
+        self._reserved = False
         if self.world > 1:
             engine.layer_grad_hook = self._on_layer
 
-    def _reduce(self, t: torch.Tensor):
+    # ------------------------------------------------------------------ ranges
+    def _clip(self, lo: int, hi: int):
+        """[lo, hi) restricted to what must be reduced (everything, or the optimizer's ranges)."""
+        if hi <= lo:
+            return []
+        if self.owned is None:
+            return [(lo, hi)]
+        out = []
+        for a, b in self.owned:
+            a2, b2 = max(a, lo), min(b, hi)
+            if b2 > a2:
+                if out and a2 - out[-1][1] < 1024:      # bridge alignment padding: fewer, larger collectives
+                    out[-1] = (out[-1][0], b2)
+                else:
+                    out.append((a2, b2))
+        return out
+
+    def tail_ranges(self):
+        f = self.engine.flat
+        lo = f.layer_ranges[-1][1] if f.layer_ranges else 0
+        first = f.layer_ranges[0][0] if f.layer_ranges else 0
+        return self._clip(0, first) + self._clip(lo, f.total)
+
+    def _reduce(self, t: torch.Tensor, tail: bool = False):
+        group = self.tail_group if tail else self.group
         if not t.is_cuda:
             # host tensors (gloo; the CPU tests of this bookkeeping): synchronous SUM then 1/world
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=group)
             t.div_(self.world)
             return
+        side = self.tail_side if tail else self.side
         ev = torch.cuda.Event()
         ev.record()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ev)
-            self.works.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True))
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            w = self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=group, async_op=True)
+        (self.tail_works if tail else self.works).append(w)
 
     def _on_layer(self, i: int):
         a, b = self.engine.flat.layer_ranges[i]
         self.done_layers.add(i)
-        self._reduce(self.engine.flat.G[a:b])
+        for a2, b2 in self._clip(a, b):
+            self._reduce(self.engine.flat.G[a2:b2])
+        if self.reserve_sms and not self._reserved and self.engine.flat.G.is_cuda:
+            ops.set_sm_reserve(self.reserve_sms)
+            self._reserved = True
 
-    def finish(self):
-        """Reduce everything outside the per-layer slices (heads, fusion, embeddings), then wait."""
+    # ------------------------------------------------------------------ end of backward
+    def launch_tail(self):
+        """Issue what backward could not: layers whose hook never fired, then the tail ranges."""
         if self.world <= 1:
             return
         f = self.engine.flat
-        lo = f.layer_ranges[-1][1] if f.layer_ranges else 0
-        first = f.layer_ranges[0][0] if f.layer_ranges else 0
-        if first > 0:
-            self._reduce(f.G[:first])
         for i, (a, b) in enumerate(f.layer_ranges):
             if i not in self.done_layers:
-                self._reduce(f.G[a:b])
-        self._reduce(f.G[lo:])
+                for a2, b2 in self._clip(a, b):
+                    self._reduce(f.G[a2:b2])
+        for a, b in self.tail_ranges():
+            self._reduce(f.G[a:b], tail=True)
+
+    def wait_layers(self):
+        if self._reserved:
+            ops.set_sm_reserve(0)
+            self._reserved = False
         for w in self.works:
             w.wait()
         self.works.clear()
         self.done_layers.clear()
+
+    def wait_tail(self):
+        for w in self.tail_works:
+            w.wait()
+        self.tail_works.clear()
+
+    def finish(self):
+        """Reduce everything backward has not reduced yet, then wait for all of it."""
+        if self.world <= 1:
+            return
+        self.launch_tail()
+        self.wait_layers()
+        self.wait_tail()

@@ -51,12 +51,64 @@ def _worker(rank, world, port, fired, q):
                 covered[a:b] = True
             covered[640:] = True
             assert torch.allclose(eng.flat.G[covered], expect[covered], atol=1e-6), "step %d" % step
-            assert not sync.works and not sync.done_layers
+            assert not sync.works and not sync.tail_works and not sync.done_layers
         q.put((rank, "ok"))
     except Exception as e:                                       # pragma: no cover
         q.put((rank, repr(e)))
     finally:
         dist.destroy_process_group()
+
+
+def _worker_owned(rank, world, port, q):
+    """GradSync(optimizer=...): only the ranges the optimizer updates are reduced; launch_tail / wait_layers /
+    wait_tail (the split FlatAdamW.step(sync=...) uses) cover every owned element exactly once."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mtvaf_b200.optim import GradSync
+        layer_ranges = [(0, 4096), (4096, 8192)]
+        total = 32768
+        # owned: both layers, a head range right after them, and the embedding tables at the end; the 8192+2048..20000
+        # stretch (ANP heads / projectors / probe in the real model) is never stepped
+        owned = [(0, 8192, 5e-5, 1e-2), (8192, 10240, 5e-2, 1e-2), (20000, 32768, 5e-5, 1e-2)]
+        opt = SimpleNamespace(ranges=owned)
+        eng = _fake_engine(total, layer_ranges, rank)
+        mine = eng.flat.G.clone()
+        expect = sum(_fake_engine(total, layer_ranges, r).flat.G for r in range(world)) / world
+        sync = GradSync(eng, optimizer=opt)
+        assert sync.tail_ranges() == [(8192, 10240), (20000, 32768)]
+        eng.layer_grad_hook(1)
+        sync.launch_tail()                                       # layer 0 never fired: must be picked up here
+        sync.wait_layers()
+        sync.wait_tail()
+        m = torch.zeros(total, dtype=torch.bool)
+        for a, b, _, _ in owned:
+            m[a:b] = True
+        assert torch.allclose(eng.flat.G[m], expect[m], atol=1e-6)
+        assert torch.equal(eng.flat.G[~m], mine[~m])             # rank-local: untouched
+        assert not sync.works and not sync.tail_works and not sync.done_layers
+        q.put((rank, "ok"))
+    except Exception as e:                                       # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradsync_optimizer_owned_ranges_world2_gloo():
+    from mtvaf_b200 import build
+    build.build()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_owned, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
 
 
 @pytest.mark.parametrize("fired", [(2, 1, 0), (2,), ()])

@@ -1,7 +1,7 @@
 """Runs every hot kernel variant of the training step at the bench shape (B=256, L=128, P=16, bf16) twice, so one
 
-  ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16_tc2|attn_|layernorm_bwd' \
-      --launch-skip <n_variants> -o gpurun_out/hot python tools/profile_hot_kernels.py
+  ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:'gemm_bf16_tc2|attn_|layernorm_bwd' -o gpurun_out/hot python tools/profile_hot_kernels.py
 
 captures each of them warm, once.  Prints the launch order (one name per kernel) so reports can be matched."""
 import os
@@ -67,11 +67,14 @@ def main():
     if only:
         variants = [v for v in variants if v[0] in only.split(",")]
     for rep in range(2):
+        if rep == 1:
+            torch.cuda.profiler.start()          # ncu --profile-from-start off: capture the warm pass only
         for name, fn in variants:
             fn()
             torch.cuda.synchronize()
             if rep == 1:
                 print(name, flush=True)
+    torch.cuda.profiler.stop()
 
 
 if __name__ == "__main__":
