@@ -131,7 +131,7 @@ def cpu_reference_run(batch_size: int, steps: int, warmup: int):
     return batch_size / med, med, torch.get_num_threads()
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
@@ -146,17 +146,27 @@ def run_reference(args, rank, world):
                              "sample": "%d fwd+bwd steps of batch %d, L=128 (oracle restatement of the reference, "
                                        "fp32, torch CPU eager)" % (steps, args.cpu_sample_batch)},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner) write there too, so everything
+    # before the final print goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the mtvaf_b200 hot path has no CPU fallback")
@@ -164,7 +174,7 @@ def main():
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     layer_ctas = int(os.environ.get("MTVAF_NCCL_CTAS", 4))
-    tail_ctas = int(os.environ.get("MTVAF_TAIL_CTAS", 32))
+    tail_ctas = int(os.environ.get("MTVAF_TAIL_CTAS", 16))
     reserve = int(os.environ.get("MTVAF_SM_RESERVE", 2 * layer_ctas))
     tail_group = None
     if world > 1:
@@ -208,7 +218,14 @@ def main():
     eng.base_seed = 0x5EED + rank                        # different dropout streams per rank
     total_steps = args.warmup + 2 * args.steps + 8
     opt = FlatAdamW(eng, lr=LR, warmup_steps=max(1, total_steps // 100), total_steps=total_steps * 50)
-    sync = GradSync(eng, tail_group=tail_group, optimizer=opt, reserve_sms=reserve) if world > 1 else None
+    sync = GradSync(eng, tail_group=tail_group, optimizer=opt, reserve_sms=reserve,
+                    tail_reserve_sms=tail_ctas if tail_group is not None else 0) if world > 1 else None
+    dp_debug = os.environ.get("MTVAF_DP_DEBUG", "")          # diagnostics only (never set by the driver)
+    if dp_debug == "nosync":
+        eng.layer_grad_hook = None
+        sync = None                                          # N independent replicas: isolates clock / power effects
+    elif dp_debug == "tailonly" and sync is not None:
+        eng.layer_grad_hook = None                           # everything reduced after backward: exposed comm time
 
     # distinct synthetic batches per rank (DistributedSampler-style disjoint shards), pinned on the host
     n_host = 4
@@ -364,7 +381,7 @@ def main():
                                    "configs[1])",
                        "per_gpu_batch": B, "global_batch": B * world, "seq_len": L_TEXT, "prefix_rows": 16,
                        "parallelism": "dp%d" % world,
-                       "dp": None if world == 1 else {"layer_allreduce_ctas": layer_ctas, "tail_allreduce_ctas": tail_ctas
+                       "dp": None if world == 1 else {"debug": dp_debug or None, "layer_allreduce_ctas": layer_ctas, "tail_allreduce_ctas": tail_ctas
                                                       if tail_group is not None else layer_ctas,
                                                       "sm_reserve_during_backward": reserve,
                                                       "reduced": "optimizer-owned ranges only"},
@@ -392,7 +409,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": "3 fwd+bwd steps of batch %d, L=128 (oracle restatement, fp32 torch "
                                               "CPU eager; no optimizer step)" % args.cpu_sample_batch}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # tear down in dependency order: the captured graph holds NCCL kernels of this communicator
         if graphed is not None:

@@ -12,10 +12,13 @@
 //     d along the lanes = coalesced fp32 rows of dK_p / dV_p;
 //   * TMEM (512 columns): S [0,144) | dP [144,288) | dQ [288,352) | dK [352,416) | dV [416,480) |
 //     dK_p^T [480,496) | dV_p^T [496,512): the S / dP columns of item i+1 never alias the gradients of item i.
-// Warp roles (544 threads): warps 0..15 SIMT (thread = query row x quarter of the 8-key units), warp 16 lane 0 =
-// TMA + MMA issue.  Shared memory: Q, K, dO double-buffered, V single (free again once dP = dO V^T has retired),
-// P and dS single (free once the item's gradient MMAs have retired).  Everything is handed over through
-// mbarriers; the SIMT warps synchronise among themselves with a named barrier.
+// Warp roles (672 threads): warps 0..15 SIMT softmax (thread = query row x quarter of the 8-key units), warp 16
+// lane 0 = TMA + MMA issue, warps 17..20 = DRAIN (one per TMEM lane quadrant: gradients of item i leave TMEM for
+// global memory while the softmax warps are already working on item i+1 -- with the drain inside the softmax
+// warps the per-item critical path was softmax + MMA + drain, 9.4 us per item with the tensor pipe 9 % busy,
+// profiles/r1_ncu_hot_v7.md).  Shared memory: Q, K, dO double-buffered, V single (free again once
+// dP = dO V^T has retired), P and dS single (free once the item's gradient MMAs have retired).  Everything is
+// handed over through mbarriers; the softmax warps synchronise among themselves with a named barrier.
 #include "attention_tc.cuh"
 
 namespace mtvaf {
@@ -24,7 +27,8 @@ using namespace ptx;
 namespace {
 
 constexpr int kSimtThreads = 512;
-constexpr int kPipeThreads = kSimtThreads + 32;
+constexpr int kDrainWarps = 4;
+constexpr int kPipeThreads = kSimtThreads + 32 + kDrainWarps * 32;
 constexpr float kLog2eP = 1.4426950408889634f;
 // TMEM columns
 constexpr int TC_S = 0, TC_DP = 144, TC_DQ = 288, TC_DK = 352, TC_DV = 416, TC_DKP = 480, TC_DVP = 496;
@@ -90,7 +94,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* bar_s = bars + 5;     //     S and dP in TMEM            (tcgen05.commit)
   uint64_t* bar_p = bars + 6;     //     P and dS in smem, S/dP read (16 warp arrivals)
   uint64_t* bar_g = bars + 7;     //     gradients in TMEM           (tcgen05.commit)
-  uint64_t* bar_o = bars + 8;     //     gradients drained           (16 warp arrivals)
+  uint64_t* bar_o = bars + 8;     //     gradients drained           (4 drain-warp arrivals)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,7 +110,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_p, 16);
     mbar_init(bar_g, 1);
-    mbar_init(bar_o, 16);
+    mbar_init(bar_o, kDrainWarps);
     fence_barrier_init();
   }
   __syncwarp();
@@ -228,6 +232,62 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
     __syncwarp();
+  } else if (warp > 16) {
+    // ============================================ drain warps =============================================
+    // warp 17 + q' owns TMEM lanes [32 * quad, +32) with quad = warp & 3 (the lane quadrant a warp may access)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                  // query / key row == TMEM lane (head-dim index for the prefix)
+    const bool row_ok = row < a.L;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    int il = 0;
+    for (int item = first; item < n_items; item += gridDim.x, ++il) {
+      const int b = item / a.nh, h = item - b * a.nh;
+      mbar_wait(bar_g, il & 1);                        // this item's gradient MMAs have retired
+      tc_fence_after();
+      // dQ | dK | dV of the text rows: lane = row, 64 head-dim columns each = one full 128-byte line per lane
+#pragma unroll
+      for (int which = 0; which < 3; ++which) {
+        const int tc = which == 0 ? TC_DQ : (which == 1 ? TC_DK : TC_DV);
+        __nv_bfloat16* dst = dqkv + ((long long)b * a.L + row) * ld_dqkv + which * H + h * 64;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + tc + hf * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            uint4* o = reinterpret_cast<uint4*>(dst + hf * 32);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+              w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+              w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+              w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+              o[v] = w;
+            }
+          }
+        }
+      }
+      // prefix rows, transposed accumulators: lane = head-dim index d (TMEM lanes 0..63), column = prefix key
+      if (a.P8 > 0 && quad < 2) {                        // warp-uniform
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          float* dst = which ? dvp : dkp;
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_row + (which ? TC_DVP : TC_DKP), r);
+          tmem_ld_wait();
+          if (dst) {
+            float* o = dst + ((long long)b * a.nh + h) * a.P * 64 + row;      // row == d here
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < a.P) o[j * 64] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_o);
+    }
   } else {
     // ============================================ SIMT warps ==============================================
     const int quad = warp & 3, part = warp >> 2;       // TMEM lane group / quarter of the columns
@@ -262,62 +322,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         o0 = po[0];
         o1 = po[1];
       }
-    };
-    // drain the gradients of `item` from TMEM (bar_g of that item has been awaited by the caller)
-    auto store_item = [&](int item) {
-      const int b = item / a.nh, h = item - b * a.nh;
-      uint32_t r[16];
-      // dQ
-      tmem_ld_32x32b_x16(t_row + TC_DQ + dcol, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        uint4* o = reinterpret_cast<uint4*>(dqkv + ((long long)b * a.L + row) * ld_dqkv + h * 64 + dcol);
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-          w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-          w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-          w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
-          o[v] = w;
-        }
-      }
-      // dK, dV of the text keys: lane = key row
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        __syncwarp();
-        tmem_ld_32x32b_x16(t_row + (which ? TC_DV : TC_DK) + dcol, r);
-        tmem_ld_wait();
-        if (row_ok) {
-          uint4* o = reinterpret_cast<uint4*>(dqkv + ((long long)b * a.L + row) * ld_dqkv + (which + 1) * H + h * 64 +
-                                              dcol);
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-            w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-            w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-            w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
-            o[v] = w;
-          }
-        }
-      }
-      // prefix rows, transposed accumulators: lane = head-dim index d (lanes 0..63), column = prefix key
-      if (a.P8 > 0 && part < 2 && quad < 2) {            // warp-uniform
-        float* dst = part ? dvp : dkp;
-        __syncwarp();
-        tmem_ld_32x32b_x16(t_row + (part ? TC_DVP : TC_DKP), r);
-        tmem_ld_wait();
-        if (dst) {
-          float* o = dst + ((long long)b * a.nh + h) * a.P * 64 + row;      // row == d here
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < a.P) o[j * 64] = __uint_as_float(r[j]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_o);
     };
 
     float m_next = 0.f, lse_next = 0.f;
@@ -363,13 +367,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         lse_next = fetch_lse(next);
         fetch_o(next, o0n, o1n);
       }
-      // ---- drain the previous item's gradients (its MMAs were issued one softmax ago); this also guarantees
-      //      that P / dS in shared memory are free again
-      if (prev >= 0) {
-        mbar_wait(bar_g, ph ^ 1);
-        tc_fence_after();
-        store_item(prev);
-      }
+      // ---- P / dS in shared memory are free again once the previous item's gradient MMAs have retired (the
+      //      drain warps take those gradients out of TMEM meanwhile)
+      if (prev >= 0) mbar_wait(bar_g, ph ^ 1);
       simt_barrier();                                    // publishes sMask and sExch
       const float dsum = (sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row]);
       const uint32_t rowkey =
@@ -436,11 +436,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
       prev = item;
-    }
-    if (prev >= 0) {
-      mbar_wait(bar_g, (il - 1) & 1);
-      tc_fence_after();
-      store_item(prev);
     }
   }
   tc_fence_before();

@@ -101,7 +101,10 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const fl
   const int stride = gridDim.x * LN_WARPS;
   int row = blockIdx.x * LN_WARPS + warp;
   typename V::Raw rz[NV], rg[NV];
-  if (row < rows) {
+  float mean_n = 0.f, rstd_n = 0.f;              // the row statistics travel with the row (they were 24 % of all
+  if (row < rows) {                              // stall samples when loaded at first use, profiles/r1_ncu_hot_v7.md)
+    mean_n = __ldg(mean_in + row);
+    rstd_n = __ldg(rstd_in + row);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = (v * 32 + lane) * 8;
@@ -112,9 +115,11 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const fl
     float x[NV][8], g[NV][8];
 #pragma unroll
     for (int v = 0; v < NV; ++v) { V::cvt(rz[v], x[v]); V::cvt(rg[v], g[v]); }
-    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float mean = mean_n, rstd = rstd_n;
     const int nrow = row + stride;
     if (nrow < rows) {
+      mean_n = __ldg(mean_in + nrow);
+      rstd_n = __ldg(rstd_in + nrow);
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = (v * 32 + lane) * 8;

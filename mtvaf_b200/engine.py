@@ -202,7 +202,7 @@ class Engine:
         self.step_counter = 0
         self.base_seed = 0x5EED
         self.layer_grad_hook: Optional[Callable[[int], None]] = None   # DP: called when layer i's grads are final
-        self.tail_grad_hook: Optional[Callable[[], None]] = None
+        self.tail_grad_hook: Optional[Callable[[], None]] = None       # DP: called when the embedding grads are final
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -376,6 +376,8 @@ class Engine:
                                  f.g(e + "embeddings.token_type_embeddings.weight"),
                                  f.g(e + "embeddings.LayerNorm.weight"), f.g(e + "embeddings.LayerNorm.bias"),
                                  p_h, sd(1))
+                if self.tail_grad_hook:
+                    self.tail_grad_hook()      # DP: the embedding tables' gradients are final
             elif want_dembeds:
                 d_embeds = dy
         return dkv, d_embeds

@@ -148,7 +148,7 @@ class GradSync:
        or: sync = GradSync(engine); loss.backward(); sync.finish(); optimizer.step()"""
 
     def __init__(self, engine: Engine, group=None, tail_group=None, optimizer: Optional["FlatAdamW"] = None,
-                 reserve_sms: int = 0):
+                 reserve_sms: int = 0, tail_reserve_sms: int = 0):
         import torch.distributed as dist
         self.dist = dist
         self.engine = engine
@@ -164,9 +164,17 @@ class GradSync:
         # SMs the persistent kernels leave alone while layer all-reduces are resident (mtvaf_set_sm_reserve): set
         # when the first layer hook fires, cleared in wait_layers()
         self.reserve_sms = reserve_sms
+        self.tail_reserve_sms = tail_reserve_sms
         self._reserved = False
+        self._emb_lo = None        # start of the embedding tables in the flat buffer (they are packed last)
+        self._emb_done = False
+        flat = engine.flat
+        emb = [n for n in getattr(flat, "names", []) if ".embeddings." in n or n.startswith("embeddings.")]
+        if emb and max(flat.offsets[n][0] + flat.offsets[n][1] for n in emb) + 64 >= flat.total:
+            self._emb_lo = min(flat.offsets[n][0] for n in emb)
         if self.world > 1:
             engine.layer_grad_hook = self._on_layer
+            engine.tail_grad_hook = self._on_embeddings
 
     # ------------------------------------------------------------------ ranges
     def _clip(self, lo: int, hi: int):
@@ -189,7 +197,20 @@ class GradSync:
         f = self.engine.flat
         lo = f.layer_ranges[-1][1] if f.layer_ranges else 0
         first = f.layer_ranges[0][0] if f.layer_ranges else 0
-        return self._clip(0, first) + self._clip(lo, f.total)
+        hi = self._emb_lo if (self._emb_done and self._emb_lo is not None) else f.total
+        return self._clip(0, first) + self._clip(lo, hi)
+
+    def _on_embeddings(self):
+        """Called by Engine.encoder_bwd right after the embedding backward: the embedding tables are 80 % of the
+        tail, and the fusion backward that still follows hides their all-reduce."""
+        if self._emb_lo is None or self._emb_done:
+            return
+        for a, b in self._clip(self._emb_lo, self.engine.flat.total):
+            self._reduce(self.engine.flat.G[a:b], tail=True)
+        self._emb_done = True
+        if self.tail_reserve_sms and self.engine.flat.G.is_cuda:
+            ops.set_sm_reserve(max(self.tail_reserve_sms, self.reserve_sms))   # wide collective resident from here on
+            self._reserved = True
 
     def _reduce(self, t: torch.Tensor, tail: bool = False):
         group = self.tail_group if tail else self.group
@@ -241,6 +262,7 @@ class GradSync:
         for w in self.tail_works:
             w.wait()
         self.tail_works.clear()
+        self._emb_done = False
 
     def finish(self):
         """Reduce everything backward has not reduced yet, then wait for all of it."""
