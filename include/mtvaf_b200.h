@@ -174,6 +174,13 @@ int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void* qkv, int6
                         const void* vp, int P, const int64_t* key_mask, const void* ctx, int64_t ld_ctx,
                         const float* lse, int B, int L, int nh, int d, void* dqkv, int64_t ld_dqkv, float* dkp,
                         float* dvp, float* dsum_scratch, int dtype, float p_drop, uint64_t seed, void* stream);
+/* Same, plus d_bias_qkv (optional, may be NULL): fp32 [3*nh*d], += column sums of dqkv = the bias gradient of the fused
+ * Q/K/V projection (autograd of modeling_roberta.py:202,219-220).  Produced inside the pipelined tcgen05 kernel
+ * while its drain warps empty TMEM; other kernel paths run mtvaf_colsum over dqkv afterwards. */
+int mtvaf_attention_bwd_ex(const void* dctx, int64_t ld_dctx, const void* qkv, int64_t ld_qkv, const void* kp,
+                        const void* vp, int P, const int64_t* key_mask, const void* ctx, int64_t ld_ctx,
+                        const float* lse, int B, int L, int nh, int d, void* dqkv, int64_t ld_dqkv, float* dkp,
+                        float* dvp, float* dsum_scratch, int dtype, float p_drop, uint64_t seed, float* d_bias_qkv, void* stream);
 
 /* ---- visual prompt gates: get_visual_prompt bert_model.py:566-587 ----------------------------- */
 /* guids: [n_img, B, 4, 8*hid] MLP outputs (encoder_conv), each row viewed as 4 splits of 2*hid.

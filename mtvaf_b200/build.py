@@ -15,6 +15,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libmtvaf_b200.so")
+# experiments: MTVAF_EXTRA_NVCC_FLAGS="-DX=1" MTVAF_LIB_TAG=x python -m mtvaf_b200.build -> _C/libmtvaf_b200_x.so, picked up
+# by mtvaf_b200.lib when MTVAF_LIB_TAG=x is set at import time
+_TAG = os.environ.get("MTVAF_LIB_TAG", "")
+if _TAG:
+    LIB_PATH = os.path.join(OUT_DIR, "libmtvaf_b200_%s.so" % _TAG)
+    OUT_DIR = os.path.join(OUT_DIR, "obj_" + _TAG)
+FLAGS_EXTRA = os.environ.get("MTVAF_EXTRA_NVCC_FLAGS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -31,7 +38,7 @@ def _digest() -> str:
             h.update(f.encode())
             h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(open(os.path.join(os.path.dirname(HERE), "include", "mtvaf_b200.h"), "rb").read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(FLAGS + FLAGS_EXTRA).encode())
     return h.hexdigest()
 
 
@@ -45,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OUT_DIR, src[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + FLAGS_EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

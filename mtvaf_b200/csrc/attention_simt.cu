@@ -521,11 +521,14 @@ extern "C" int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* 
   return 0;
 }
 
-extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void* qkv, int64_t ld_qkv,
-                                   const void* kp, const void* vp, int P, const int64_t* key_mask, const void* ctx,
-                                   int64_t ld_ctx, const float* lse, int B, int L, int nh, int d, void* dqkv,
-                                   int64_t ld_dqkv, float* dkp, float* dvp, float* dsum_scratch, int dtype,
-                                   float p_drop, uint64_t seed, void* stream) {
+// d_bias_qkv (optional): fp32 [3 * nh * d], += column sums of dqkv -- the bias gradient of the fused QKV projection
+// (models/modeling_roberta.py:202,219-220).  The pipelined tcgen05 kernel produces it while draining TMEM; every other
+// path runs the column-sum kernel over dqkv afterwards, so callers see one behaviour.
+extern "C" int mtvaf_attention_bwd_ex(const void* dctx, int64_t ld_dctx, const void* qkv, int64_t ld_qkv,
+                                      const void* kp, const void* vp, int P, const int64_t* key_mask, const void* ctx,
+                                      int64_t ld_ctx, const float* lse, int B, int L, int nh, int d, void* dqkv,
+                                      int64_t ld_dqkv, float* dkp, float* dvp, float* dsum_scratch, int dtype,
+                                      float p_drop, uint64_t seed, float* d_bias_qkv, void* stream) {
   AttnArgs a;
   if (int rc = fill_args(&a, qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, d, p_drop, seed, dtype)) return rc;
   MTVAF_REQUIRE(dctx && ctx && lse && dqkv && dsum_scratch, "attention_bwd: null argument");
@@ -541,9 +544,11 @@ extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void
     bool ok = false;
     if (int rc = attn_tc_prepare(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, p_drop, seed, &ta, &tm, &ok)) return rc;
     if (ok && attention_impl_override() == 0 && attn_bwd_pipe_supported(ta))
-      return attn_bwd_pipe_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st);
-    if (ok && attn_bwd_tc_supported(ta))
-      return attn_bwd_tc_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st);
+      return attn_bwd_pipe_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, d_bias_qkv, st);
+    if (ok && attn_bwd_tc_supported(ta)) {
+      if (int rc = attn_bwd_tc_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st)) return rc;
+      return d_bias_qkv ? mtvaf_colsum(dqkv, ld_dqkv, dtype, B * L, 3 * nh * d, d_bias_qkv, stream) : 0;
+    }
   }
   if (dtype == MTVAF_BF16) {
     using T = __nv_bfloat16;
@@ -561,5 +566,14 @@ extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void
     attn_bwd_dkv_kernel<T><<<gk, 128, 0, st>>>(a, (const T*)dctx, ld_dctx, lse, dsum_scratch, (T*)dqkv, ld_dqkv, dkp, dvp);
   }
   MTVAF_LAUNCH_CHECK();
-  return 0;
+  return d_bias_qkv ? mtvaf_colsum(dqkv, ld_dqkv, dtype, B * L, 3 * nh * d, d_bias_qkv, stream) : 0;
+}
+
+extern "C" int mtvaf_attention_bwd(const void* dctx, int64_t ld_dctx, const void* qkv, int64_t ld_qkv,
+                                   const void* kp, const void* vp, int P, const int64_t* key_mask, const void* ctx,
+                                   int64_t ld_ctx, const float* lse, int B, int L, int nh, int d, void* dqkv,
+                                   int64_t ld_dqkv, float* dkp, float* dvp, float* dsum_scratch, int dtype,
+                                   float p_drop, uint64_t seed, void* stream) {
+  return mtvaf_attention_bwd_ex(dctx, ld_dctx, qkv, ld_qkv, kp, vp, P, key_mask, ctx, ld_ctx, lse, B, L, nh, d, dqkv,
+                                ld_dqkv, dkp, dvp, dsum_scratch, dtype, p_drop, seed, nullptr, stream);
 }

@@ -35,9 +35,10 @@ int attn_bwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dct
                        cudaStream_t st);
 // software-pipelined backward for the reference shape (L <= 128, P <= 16): attention_tc_bwd_pipe.cu
 bool attn_bwd_pipe_supported(const AttnTcArgs& a);
+// dbias (optional): fp32 [3 * nh * 64], += column sums of dqkv (bias gradient of the fused QKV projection)
 int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                          int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
-                         cudaStream_t st);
+                         float* dbias, cudaStream_t st);
 int attention_impl_override();   // 0 = auto (tcgen05 when the shape fits), 1 = SIMT only, 2 = tcgen05 without the pipelined bwd
 
 }  // namespace mtvaf

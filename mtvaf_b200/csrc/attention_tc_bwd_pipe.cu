@@ -75,7 +75,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmKp, const __grid_constant__ CUtensorMap tmVp,
                      const __grid_constant__ CUtensorMap tmdO, AttnTcArgs a, const float* __restrict__ lse,
                      const __nv_bfloat16* __restrict__ ctx, long long ld_ctx, __nv_bfloat16* __restrict__ dqkv,
-                     long long ld_dqkv, float* __restrict__ dkp, float* __restrict__ dvp) {
+                     long long ld_dqkv, float* __restrict__ dkp, float* __restrict__ dvp, float* __restrict__ dbias) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const PipeSmem lay = pipe_layout(a.P8, a.L64);
@@ -266,6 +266,25 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               o[v] = w;
             }
           }
+          if (dbias) {                                   // kernel-uniform
+            // bias gradient of the fused QKV projection: column sums over this warp's 32 rows (transpose-reduce, 31
+            // shuffles: after the stage with stride s a lane keeps the columns whose bit s equals its own), then one
+            // fp32 reduction per column.  Replaces a separate pass over dqkv (the drain warps are off the critical path).
+            float c[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) c[i] = row_ok ? __uint_as_float(r[i]) : 0.f;
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+              const bool up = (lane & st) != 0;
+#pragma unroll
+              for (int i = 0; i < st; ++i) {
+                const float send = up ? c[i] : c[i + st];
+                const float keep = up ? c[i + st] : c[i];
+                c[i] = keep + __shfl_xor_sync(0xffffffffu, send, st);
+              }
+            }
+            atomicAdd(dbias + which * H + h * 64 + hf * 32 + lane, c[0]);
+          }
         }
       }
       // prefix rows, transposed accumulators: lane = head-dim index d (TMEM lanes 0..63), column = prefix key
@@ -300,7 +319,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int units = NS >> 3;
     const int dcol = part * 16;
     const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
-    const float ds_coef = a.scale / a.drop_scale;      // dS = P' * (scale / drop_scale) * (dP' - D)
 
     // smem key `k`: text row k (k < L64), prefix row k - NT (k >= NT)
     auto fetch_mask = [&](int item) -> float {
@@ -371,7 +389,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       //      drain warps take those gradients out of TMEM meanwhile)
       if (prev >= 0) mbar_wait(bar_g, ph ^ 1);
       simt_barrier();                                    // publishes sMask and sExch
-      const float dsum = (sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row]);
+      // dS = P' (scale / drop_scale) (drop_scale dP_raw - D) = P' * scale * (dP_raw - D / drop_scale)
+      const float dsum_s = ((sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row])) / a.drop_scale;
+      const float ds_c = a.scale;
       const uint32_t rowkey =
           a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
 
@@ -390,13 +410,13 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < 8; ++j) {
           // masked / absent keys and rows past L give exp2(-inf) = 0 (S and dP are finite: padded K/V rows are 0)
           p[j] = pipe_ex2(fmaf(__uint_as_float(rs[j]), sc2, mk[j] - lse2));
-          dp[j] = __uint_as_float(rd[j]) * a.drop_scale;
-          ds[j] = p[j] * ds_coef;
+          dp[j] = __uint_as_float(rd[j]);                // raw dP' / drop_scale: the scale is folded into ds_c / dsum_s
+          ds[j] = p[j] * ds_c;
         }
         // reference key numbering for the dropout hash: prefix rows 0..P-1, then the text rows
         if (a.drop_thr) attn_drop_apply8(rowkey, c < NT ? a.P + c : c - NT, a.drop_thr, p, dp);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ds[j] *= dp[j] - dsum;
+        for (int j = 0; j < 8; ++j) ds[j] *= dp[j] - dsum_s;
         const uint32_t off = (u >> 3) * 16384 + prow_off + (((u & 7) ^ row8) << 4);
         uint4 w;
         w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
@@ -455,7 +475,7 @@ bool attn_bwd_pipe_supported(const AttnTcArgs& a) {
 
 int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                          int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
-                         cudaStream_t st) {
+                         float* dbias, cudaStream_t st) {
   MTVAF_REQUIRE(ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0,
                 "attention_bwd(pipe): dqkv must be 16-byte aligned with ld %% 8 == 0");
   MTVAF_REQUIRE(ld_ctx % 8 == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
@@ -475,7 +495,7 @@ int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* d
   const int grid = n_items < sm_count() ? n_items : sm_count();
   attn_bwd_pipe_kernel<<<grid, kPipeThreads, lay.total, st>>>(m.q, m.kv, m.kp, m.vp, tmdO, a, lse,
                                                              (const __nv_bfloat16*)ctx, ld_ctx, (__nv_bfloat16*)dqkv,
-                                                             ld_dqkv, dkp, dvp);
+                                                             ld_dqkv, dkp, dvp, dbias);
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -212,34 +212,43 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32
 }
 
 // ---- attention-probability dropout (modeling_roberta.py:268) -----------------------------------
-// The softmax kernels are issue-bound, so the mask costs ~4 integer ops per element: one 32-bit key per
-// (batch, head, query) row (attn_drop_rowkey, hashed once per row) and one 3-multiply hash per PAIR of keys
-// (reference key numbering: prefix rows 0..P-1, then text rows).  Forward, backward and the SIMT kernels all
-// derive the mask from these two functions, so backward regenerates forward's mask.
+// The softmax kernels are issue-bound (profiles/r1_ncu_hot_v7.md: 21 instructions per element in the backward
+// loop, 9 of them mask arithmetic), so the mask costs < 3 integer ops per element: one 32-bit key per
+// (batch, head, query) row (attn_drop_rowkey, hashed once per row) and ONE hash per QUAD of keys whose
+// 32x64 -> 64-bit product is consumed as four fields: lo, lo << 16, hi, hi << 16, each compared with the full
+// 32-bit threshold (fields 0 / 2 are exact to 2^-32, fields 1 / 3 have 16-bit resolution: |dp| <= 1.6e-5).
+// Reference key numbering: prefix rows 0..P-1, then text rows.  Forward, backward and the SIMT kernels all
+// derive the mask from these functions, so backward regenerates forward's mask.
 __device__ __forceinline__ uint32_t attn_drop_rowkey(uint64_t seed, uint64_t row) { return dropout_bits(seed, row); }
-__device__ __forceinline__ void attn_drop_pair(uint32_t rowkey, uint32_t pair, uint32_t& h0, uint32_t& h1) {
-  uint32_t h = (pair ^ rowkey) * 0x9E3779B1u;
+__device__ __forceinline__ void attn_drop_quad(uint32_t rowkey, uint32_t quad, uint32_t (&f)[4]) {
+  uint32_t h = (quad ^ rowkey) * 0x9E3779B1u;
   h ^= h >> 15;
-  h *= 0x85EBCA77u;
-  h0 = h;
-  h ^= h >> 16;
-  h1 = h * 0xC2B2AE3Du;
+  // low 64 bits of h x (64-bit odd constant): IMAD.WIDE.U32 + IMAD.  A 32-bit multiplier would leave the high word
+  // in [0, C) instead of [0, 2^32) (measured: keep rate 0.868 instead of 0.9 for that field)
+  const unsigned long long w = static_cast<unsigned long long>(h) * 0x85EBCA77C2B2AE3Dull;
+  const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
+  f[0] = lo;
+  f[1] = lo << 16;
+  f[2] = hi;
+  f[3] = hi << 16;
 }
 __device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int kk, uint32_t thr) {
-  uint32_t h0, h1;
-  attn_drop_pair(rowkey, static_cast<uint32_t>(kk) >> 1, h0, h1);
-  return ((kk & 1) ? h1 : h0) >= thr;
+  uint32_t f[4];
+  attn_drop_quad(rowkey, static_cast<uint32_t>(kk) >> 2, f);
+  const int i = kk & 3;
+  return (i == 0 ? f[0] : i == 1 ? f[1] : i == 2 ? f[2] : f[3]) >= thr;
 }
-// zero the dropped entries among the 8 consecutive keys kk0 .. kk0+7 (kk0 >= 0) of v (and w): the hash of a pair
-// is consumed as predicates right away (no flag array in registers); the 1/(1-p) scale is the caller's business
+// zero the dropped entries among the 8 consecutive keys kk0 .. kk0+7 (kk0 >= 0) of v (and w): the fields of a quad
+// are consumed as predicates right away (no flag array in registers); the 1/(1-p) scale is the caller's business
 __device__ __forceinline__ void attn_drop_apply8(uint32_t rowkey, int kk0, uint32_t thr, float (&v)[8]) {
-  if ((kk0 & 1) == 0) {
+  if ((kk0 & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t h0, h1;
-      attn_drop_pair(rowkey, static_cast<uint32_t>(kk0 >> 1) + i, h0, h1);
-      if (h0 < thr) v[2 * i] = 0.f;
-      if (h1 < thr) v[2 * i + 1] = 0.f;
+    for (int i = 0; i < 2; ++i) {
+      uint32_t f[4];
+      attn_drop_quad(rowkey, static_cast<uint32_t>(kk0 >> 2) + i, f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (f[j] < thr) v[4 * i + j] = 0.f;
     }
   } else {
 #pragma unroll
@@ -248,13 +257,14 @@ __device__ __forceinline__ void attn_drop_apply8(uint32_t rowkey, int kk0, uint3
   }
 }
 __device__ __forceinline__ void attn_drop_apply8(uint32_t rowkey, int kk0, uint32_t thr, float (&v)[8], float (&w)[8]) {
-  if ((kk0 & 1) == 0) {
+  if ((kk0 & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t h0, h1;
-      attn_drop_pair(rowkey, static_cast<uint32_t>(kk0 >> 1) + i, h0, h1);
-      if (h0 < thr) { v[2 * i] = 0.f; w[2 * i] = 0.f; }
-      if (h1 < thr) { v[2 * i + 1] = 0.f; w[2 * i + 1] = 0.f; }
+    for (int i = 0; i < 2; ++i) {
+      uint32_t f[4];
+      attn_drop_quad(rowkey, static_cast<uint32_t>(kk0 >> 2) + i, f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (f[j] < thr) { v[4 * i + j] = 0.f; w[4 * i + j] = 0.f; }
     }
   } else {
 #pragma unroll

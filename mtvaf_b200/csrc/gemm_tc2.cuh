@@ -106,7 +106,11 @@ struct Gemm2Smem {
   static constexpr int kEpiBytes = kEpiWarps * StagedEpi<EPI>::kBytesPerWarp;   // staging + aux boxes
   static constexpr int kBarrierBytes = 512;
   static constexpr int kAvail = 227 * 1024 - 1024 - kBarrierBytes - kEpiBytes;
-  static constexpr int kStages = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
+#ifndef MTVAF_GEMM_MAX_STAGES
+#define MTVAF_GEMM_MAX_STAGES 8            // experiments: -DMTVAF_GEMM_MAX_STAGES=n caps the operand ring
+#endif
+  static constexpr int kStages =
+      (kAvail / kStageBytes) > MTVAF_GEMM_MAX_STAGES ? MTVAF_GEMM_MAX_STAGES : (kAvail / kStageBytes);
   static constexpr int kTotal = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;
   static_assert(kStages >= 3, "not enough shared memory for the operand ring");
 };

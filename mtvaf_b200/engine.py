@@ -349,12 +349,13 @@ class Engine:
                 kp, vp = kv[i, 0].view(B, nh, P, d), kv[i, 1].view(B, nh, P, d)
                 if dkv is not None:
                     dkp, dvp = dkv[i, 0], dkv[i, 1]
+            # (the bias gradient of the fused QKV projection = column sums of dqkv comes out of the same call)
             dqkv = ops.attention_bwd(dctx, s["qkv"], kp, vp, mask, s["ctx"], s["lse"], B, Lq, nh, d, dkp, dvp, p_a,
-                                     sd(16 * i + 2))
+                                     sd(16 * i + 2),
+                                     d_bias=f.span(f.G, ln(_LAYER_ORDER[3]), ln(_LAYER_ORDER[5]), (3 * H,)))
             # ---- fused QKV projection
             wqkv = self.cspan(ln(_LAYER_ORDER[0]), ln(_LAYER_ORDER[2]), (3 * H, H))
             ops.linear_wgrad(dqkv, s["x"], f.span(f.G, ln(_LAYER_ORDER[0]), ln(_LAYER_ORDER[2]), (3 * H, H)))
-            ops.colsum(dqkv, f.span(f.G, ln(_LAYER_ORDER[3]), ln(_LAYER_ORDER[5]), (3 * H,)))
             dx = ops.linear_dgrad(dqkv, wqkv, mode=L.EPI_RESID, aux=dz1)
             if grad_hs[i] is not None:
                 ops.add_inplace(dx, grad_hs[i].reshape(T, H).contiguous())
@@ -492,14 +493,21 @@ class Engine:
         c, f = self.cfg, self.flat
         T, H = B * Lq, c.H
         seq = hs[c.n_layers]
-        seq32 = ops.cast_f32(seq) if seq.dtype == BF16 else seq
         p_d = 0.1 if training else 0.0                                             # self.dropout, bert_model.py:466,506
-        seq_d = ops.dropout_apply(seq32, p_d, self.seed(910)) if p_d > 0 else seq32
         n_tags = f.params["fc.weight"].shape[0]
-        if n_tags <= 48 and H % 4 == 0:
-            em = ops.skinny_linear(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
+        if seq.dtype == BF16:
+            # throughput mode: the tag head stays in bf16 on the tensor cores (fp32 accumulate, fp32 emissions).  The
+            # fp32 detour (cast + fp32 dropout + warp-per-row kernels re-streaming fc.weight per row) cost 0.39 ms per
+            # step for 0.55 GFLOP (profiles/r1_launches_v7): N = 11 wastes most of a 128-wide MMA tile, and is
+            # still 5x faster because the pass is a single 50 MB read
+            seq_d = ops.dropout_apply(seq, p_d, self.seed(910)) if p_d > 0 else seq
+            em = ops.linear_fwd(seq_d, self.cw("fc.weight"), f.w("fc.bias"), out_dtype=F32).view(B, Lq, n_tags)
         else:
-            em = ops.linear_fwd(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
+            seq_d = ops.dropout_apply(seq, p_d, self.seed(910)) if p_d > 0 else seq
+            if n_tags <= 48 and H % 4 == 0:
+                em = ops.skinny_linear(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
+            else:
+                em = ops.linear_fwd(seq_d, f.w("fc.weight"), f.w("fc.bias")).view(B, Lq, n_tags)
         crf = (f.w("crf.start_transitions"), f.w("crf.end_transitions"), f.w("crf.transitions"))
         best, lens = ops.crf_decode(em, mask, *crf)
         out = dict(emissions=em, best=best, lens=lens, loss=None, prob_loss=None)
@@ -544,7 +552,17 @@ class Engine:
         ops.add_inplace(f.g("crf.transitions"), saved["d_t"])
         de = d_em.view(T, n_tags)
         ops.colsum(de, f.g("fc.bias"))
-        if n_tags <= 16 and H % 8 == 0 and n_tags * (H // 8) <= 1536:
+        if saved["seq_d"].dtype == BF16:
+            # bf16 mode: both gradients of the head on the tensor cores.  d(emissions) is padded to 16 columns (rows of
+            # a bf16 operand must be 16-byte multiples); K = n_tags: the TMA boxes zero-fill past the 11 real tags
+            de16 = torch.zeros((T, 16 * ((n_tags + 15) // 16)), dtype=BF16, device=de.device)
+            de16[:, :n_tags].copy_(de)                                              # tiny (T x 16) cast, plumbing
+            ops.gemm(de16, saved["seq_d"], a_mn=True, b_mn=True, M=n_tags, N=H, K=T, mode=L.EPI_ATOMIC_F32,
+                     out=f.g("fc.weight"), splits=ops.wgrad_splits(n_tags, H, T, True))
+            dseq = ops.gemm(de16, self.cw("fc.weight"), b_mn=True, M=T, N=H, K=n_tags)
+            if saved["p_d"] > 0:
+                dseq = ops.dropout_apply(dseq, saved["p_d"], saved["seed_d"])
+        elif n_tags <= 16 and H % 8 == 0 and n_tags * (H // 8) <= 1536:
             # skinny head: dedicated kernels; the data gradient comes out dropout-masked in the encoder's dtype
             ops.skinny_linear_wgrad(de, saved["seq_d"], f.g("fc.weight"))
             dseq = ops.skinny_linear_dgrad(de, f.w("fc.weight"), self.compute_dtype, saved["p_d"], saved["seed_d"])

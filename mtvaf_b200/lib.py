@@ -10,6 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libmtvaf_b200.so")
+if os.environ.get("MTVAF_LIB_TAG"):          # experiment builds (mtvaf_b200/build.py)
+    LIB_PATH = os.path.join(_HERE, "_C", "libmtvaf_b200_%s.so" % os.environ["MTVAF_LIB_TAG"])
 
 F32, BF16 = 0, 1
 
@@ -57,6 +59,8 @@ SIGNATURES = {
     "mtvaf_set_attention_impl": [_i],
     "mtvaf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp,
                             _vp, _vp, _i, _f, _u64, _vp],
+    "mtvaf_attention_bwd_ex": [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp,
+                               _vp, _vp, _i, _f, _u64, _vp, _vp],
     "mtvaf_gate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "mtvaf_gate_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "mtvaf_prompt_grad_combine": [_vp, _vp, _vp, _i, _f, _u64, _i64, _i, _vp, _i, _vp],

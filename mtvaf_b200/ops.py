@@ -335,15 +335,18 @@ def attention_fwd(qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.0, seed=0, want_
 
 
 def attention_bwd(dctx, qkv, kp, vp, key_mask, ctx, lse, B, Lq, nh, d, dkp=None, dvp=None, p_drop=0.0, seed=0,
-                  dqkv=None):
+                  dqkv=None, d_bias=None):
+    """d_bias (optional): fp32 [3*nh*d], += column sums of dqkv (bias gradient of the fused QKV projection)."""
     P = 0 if kp is None else kp.shape[2]
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     scratch = torch.empty((B, nh, Lq), dtype=torch.float32, device=qkv.device)
-    _check(_raw.mtvaf_attention_bwd(dctx.data_ptr(), dctx.stride(0), qkv.data_ptr(), qkv.stride(0), _p(kp), _p(vp), P,
-                                    key_mask.data_ptr(), ctx.data_ptr(), ctx.stride(0), lse.data_ptr(), B, Lq, nh, d,
-                                    dqkv.data_ptr(), dqkv.stride(0), _p(dkp), _p(dvp), scratch.data_ptr(), dt(qkv),
-                                    p_drop, seed, _stream()), "attention_bwd")
+    if d_bias is not None:
+        assert d_bias.dtype == torch.float32 and d_bias.numel() == 3 * nh * d and d_bias.is_contiguous()
+    _check(_raw.mtvaf_attention_bwd_ex(dctx.data_ptr(), dctx.stride(0), qkv.data_ptr(), qkv.stride(0), _p(kp), _p(vp),
+                                       P, key_mask.data_ptr(), ctx.data_ptr(), ctx.stride(0), lse.data_ptr(), B, Lq,
+                                       nh, d, dqkv.data_ptr(), dqkv.stride(0), _p(dkp), _p(dvp), scratch.data_ptr(),
+                                       dt(qkv), p_drop, seed, _p(d_bias), _stream()), "attention_bwd")
     return dqkv
 
 

@@ -83,6 +83,28 @@ def test_gemm_wgrad_layout(ops, Lb, dtype, T, N, K):
     assert rel_err(dw, 2 * ref) < tol
 
 
+def test_gemm_tag_head_shapes_bf16(ops, Lb):
+    """The tag head fc 768 -> 11 (models/bert_model.py:510) on the tcgen05 GEMMs in bf16 mode: N = 11 forward with fp32
+    emissions, K = 11 data gradient, M = 11 weight gradient from a [T,16] zero-padded d(emissions) operand."""
+    T, H, n_tags = 4099, 768, 11
+    x = rnd(T, H, seed=11, dtype=torch.bfloat16)
+    w = rnd(n_tags, H, seed=12, scale=0.05, dtype=torch.bfloat16)
+    bias = rnd(n_tags, seed=13)
+    em = ops.linear_fwd(x, w, bias, out_dtype=torch.float32)
+    assert em.dtype == torch.float32 and em.shape == (T, n_tags)
+    assert rel_err(em, x.float() @ w.float().t() + bias) < 1e-2
+    de16 = torch.zeros(T, 16, dtype=torch.bfloat16, device=DEV)
+    de16[:, :n_tags] = rnd(T, n_tags, seed=14, dtype=torch.bfloat16)
+    dw = torch.zeros(n_tags, H, dtype=torch.float32, device=DEV)
+    guard = dw.clone()
+    ops.gemm(de16, x, a_mn=True, b_mn=True, M=n_tags, N=H, K=T, mode=Lb.EPI_ATOMIC_F32, out=dw,
+             splits=ops.wgrad_splits(n_tags, H, T, True))
+    assert rel_err(dw, de16[:, :n_tags].float().t() @ x.float()) < 1e-2
+    dx = ops.gemm(de16, w, b_mn=True, M=T, N=H, K=n_tags)
+    assert rel_err(dx, de16[:, :n_tags].float() @ w.float()) < 1e-2
+    assert torch.equal(guard, torch.zeros_like(guard))
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_gemm_epilogues(ops, Lb, dtype):
     M, N, K = 300, 768, 256
@@ -323,6 +345,29 @@ def test_attention_fwd_bwd(ops, dtype, B, Lq, P):
     if P:
         assert rel_err(dkp, kp.grad) < btol
         assert rel_err(dvp, vp.grad) < btol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Lq,P", [(3, 128, 16), (2, 100, 16), (3, 40, 36), (1, 200, 100)])
+def test_attention_bwd_qkv_bias_grad(ops, dtype, B, Lq, P):
+    """mtvaf_attention_bwd_ex: d_bias += column sums of dqkv on every kernel path (pipelined tcgen05 drain warps for
+    L <= 128 / P <= 16, generic tcgen05 + colsum, SIMT + colsum), accumulating into what is already there."""
+    nh, d = 12, 64
+    H = nh * d
+    qkv = rnd(B * Lq, 3 * H, seed=21, dtype=dtype)
+    kp, vp = rnd(B, nh, P, d, seed=22, dtype=dtype), rnd(B, nh, P, d, seed=23, dtype=dtype)
+    lens = torch.tensor([Lq, max(1, Lq // 2), max(1, Lq - 3)][:B])
+    mask = (torch.arange(Lq).unsqueeze(0) < lens.unsqueeze(1)).long().to(DEV)
+    ctx, lse, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=0.1, seed=5)
+    dctx = rnd(B * Lq, H, seed=24, dtype=dtype)
+    base = rnd(3 * H, seed=25)
+    d_bias = base.clone()
+    dqkv = ops.attention_bwd(dctx, qkv, kp, vp, mask, ctx, lse, B, Lq, nh, d, p_drop=0.1, seed=5, d_bias=d_bias)
+    ref = dqkv.float().sum(0)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2      # bf16: the fused path sums fp32 accumulators, dqkv is rounded
+    assert rel_err(d_bias - base, ref) < tol
+    dqkv2 = ops.attention_bwd(dctx, qkv, kp, vp, mask, ctx, lse, B, Lq, nh, d, p_drop=0.1, seed=5)
+    assert torch.equal(dqkv, dqkv2)                      # the optional output does not change the gradients
 
 
 def test_attention_dropout_consistency(ops):
