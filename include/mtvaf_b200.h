@@ -70,6 +70,10 @@ typedef struct MtvafEpilogue {
   float alpha;             /* scale applied to the accumulator first (1.0 = none)                 */
   float p_drop;            /* RESID: dropout probability (0 = off)                                */
   uint64_t seed;           /* RESID: dropout stream seed; element index = m * N + n               */
+  float* colsum;           /* optional [N] fp32: += column sums of `out` as stored (the bias gradient of the layer
+                              whose input gradient this GEMM produces, e.g. d(intermediate.dense.bias) from the
+                              x GELU' epilogue).  Summed inside the TMA-staged tcgen05 epilogue from the staging box;
+                              other kernel paths run mtvaf_colsum over `out` after the GEMM.  NULL = off.           */
 } MtvafEpilogue;
 
 /* bf16 operands, tcgen05.mma (kind::f16) with TMEM fp32 accumulators, TMA-fed, persistent.

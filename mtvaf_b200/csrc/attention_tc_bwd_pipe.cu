@@ -86,7 +86,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sK0 = smem + lay.off_k;
   uint8_t* sV = smem + lay.off_v;
   float* sMask0 = reinterpret_cast<float*>(smem + lay.off_mask);          // [2][256] additive mask * log2(e)
-  float* sExch0 = reinterpret_cast<float*>(smem + lay.off_exch);          // [2][4][128] partial rowsum(dO o O)
+  float* sD0 = reinterpret_cast<float*>(smem + lay.off_exch);             // [2][128] D_q = rowsum(dO o O), by the drain warps
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
   uint64_t* bar_qk = bars;        // [2] Q + K tiles landed (TMA tx)
   uint64_t* bar_do = bars + 2;    // [2] dO tile landed
@@ -95,7 +95,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* bar_p = bars + 6;     //     P and dS in smem, S/dP read (16 warp arrivals)
   uint64_t* bar_g = bars + 7;     //     gradients in TMEM           (tcgen05.commit)
   uint64_t* bar_o = bars + 8;     //     gradients drained           (4 drain-warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_d = bars + 9;     // [2] D_q of the item in this buffer is in smem (4 drain-warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = a.nh * 64;
@@ -111,6 +112,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(bar_p, 16);
     mbar_init(bar_g, 1);
     mbar_init(bar_o, kDrainWarps);
+    mbar_init(&bar_d[0], kDrainWarps);
+    mbar_init(&bar_d[1], kDrainWarps);
     fence_barrier_init();
   }
   __syncwarp();
@@ -239,9 +242,48 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int row = quad * 32 + lane;                  // query / key row == TMEM lane (head-dim index for the prefix)
     const bool row_ok = row < a.L;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int row8 = row & 7;
+    const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
+    // D_q = rowsum(dO o O) of `item` (whose dO tile lands in buffer `buf`): the O row comes straight from global
+    // memory (128 contiguous bytes per lane), the dO row from the TMA tile.  Done here, one item AHEAD, because in
+    // the softmax warps the prefetched O registers were spilled under the 80-register cap and the spill store
+    // waited for the global load (profiles/r1_ncu_attn_v12.md: 5 % of samples + 18 % at the barrier behind it).
+    auto compute_d = [&](int item, int buf, uint32_t parity) {
+      const int b = item / a.nh, h = item - b * a.nh;
+      mbar_wait(&bar_do[buf], parity);
+      float acc = 0.f;
+      if (row_ok) {
+        const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)b * a.L + row) * ld_ctx + h * 64);
+        const uint8_t* pd = sdO0 + buf * 16384 + prow_off;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                 // two batches of four 16-byte loads (drain warps have slack)
+          uint4 o[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o[c] = __ldg(po + hf * 4 + c);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 dv = *reinterpret_cast<const uint4*>(pd + (((hf * 4 + c) ^ row8) << 4));
+            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+            const uint32_t ow[4] = {o[c].x, o[c].y, o[c].z, o[c].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x = unpack_bf16x2(dw[j]), y = unpack_bf16x2(ow[j]);
+              acc = fmaf(x.x, y.x, acc);
+              acc = fmaf(x.y, y.y, acc);
+            }
+          }
+        }
+      }
+      sD0[buf * 128 + row] = acc;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_d[buf]);
+    };
+    if (first < n_items) compute_d(first, 0, 0);
     int il = 0;
     for (int item = first; item < n_items; item += gridDim.x, ++il) {
       const int b = item / a.nh, h = item - b * a.nh;
+      // the next item's D while the softmax warps work on this one (its buffer was last read two items ago)
+      if (item + (int)gridDim.x < n_items) compute_d(item + gridDim.x, (il + 1) & 1, ((il + 1) >> 1) & 1);
       mbar_wait(bar_g, il & 1);                        // this item's gradient MMAs have retired
       tc_fence_after();
       // dQ | dK | dV of the text rows: lane = row, 64 head-dim columns each = one full 128-byte line per lane
@@ -317,7 +359,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int row8 = row & 7;
     const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
     const int units = NS >> 3;
-    const int dcol = part * 16;
     const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
 
     // smem key `k`: text row k (k < L64), prefix row k - NT (k >= NT)
@@ -331,23 +372,11 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int b = item / a.nh, h = item - b * a.nh;
       return row_ok ? lse[((long long)b * a.nh + h) * a.L + row] * kLog2eP - log2_ds : INFINITY;
     };
-    auto fetch_o = [&](int item, uint4& o0, uint4& o1) {
-      o0 = make_uint4(0, 0, 0, 0);
-      o1 = o0;
-      if (row_ok) {
-        const int b = item / a.nh, h = item - b * a.nh;
-        const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)b * a.L + row) * ld_ctx + h * 64 + dcol);
-        o0 = po[0];
-        o1 = po[1];
-      }
-    };
 
     float m_next = 0.f, lse_next = 0.f;
-    uint4 o0n = make_uint4(0, 0, 0, 0), o1n = o0n;
     if (first < n_items) {
       m_next = fetch_mask(first);
       lse_next = fetch_lse(first);
-      fetch_o(first, o0n, o1n);
     }
     int il = 0;
     int prev = -1;
@@ -357,40 +386,20 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t ph = il & 1, ph2 = (il >> 1) & 1;
       const int next = item + gridDim.x;
       float* sMask = sMask0 + buf * 256;
-      float* sExch = sExch0 + buf * 512;
-      const uint8_t* sdO = sdO0 + buf * 16384;
-      // ---- this item's prefetched scalars; D_q = rowsum(dO o O) over this thread's 16 columns
+      // ---- this item's prefetched scalars; the next item's travel while this one is processed
       if (tid < NS) sMask[tid] = m_next;
       const float lse2 = lse_next;
-      const uint4 o0 = o0n, o1 = o1n;
-      mbar_wait(&bar_do[buf], ph2);
-      {
-        const uint8_t* pd = sdO + prow_off;
-        const uint4 d0 = *reinterpret_cast<const uint4*>(pd + (((part * 2) ^ row8) << 4));
-        const uint4 d1 = *reinterpret_cast<const uint4*>(pd + (((part * 2 + 1) ^ row8) << 4));
-        float acc = 0.f;
-        const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 x = unpack_bf16x2(dw[j]), y = unpack_bf16x2(ow[j]);
-          acc = fmaf(x.x, y.x, acc);
-          acc = fmaf(x.y, y.y, acc);
-        }
-        sExch[part * 128 + row] = acc;
-      }
-      // the next item's scalars travel while this item is processed
       if (next < n_items) {
         m_next = fetch_mask(next);
         lse_next = fetch_lse(next);
-        fetch_o(next, o0n, o1n);
       }
       // ---- P / dS in shared memory are free again once the previous item's gradient MMAs have retired (the
       //      drain warps take those gradients out of TMEM meanwhile)
       if (prev >= 0) mbar_wait(bar_g, ph ^ 1);
-      simt_barrier();                                    // publishes sMask and sExch
+      simt_barrier();                                    // publishes sMask
       // dS = P' (scale / drop_scale) (drop_scale dP_raw - D) = P' * scale * (dP_raw - D / drop_scale)
-      const float dsum_s = ((sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row])) / a.drop_scale;
+      mbar_wait(&bar_d[buf], ph2);                       // D_q of this item (drain warps, one item ahead)
+      const float dsum_s = sD0[buf * 128 + row] / a.drop_scale;
       const float ds_c = a.scale;
       const uint32_t rowkey =
           a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;

@@ -27,6 +27,7 @@ struct EpiArgs {
   float drop_scale;          // 1/(1-p)
   unsigned long long seed;
   const unsigned long long* step;   // device step counter mixed into the seed (or NULL)
+  float* colsum;                    // optional [N]: += column sums of `out` (see MtvafEpilogue)
 };
 
 inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N, int splits, EpiArgs* o) {
@@ -37,6 +38,7 @@ inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N
   o->out2 = e.out2; o->ld_out2 = e.ld_out2; o->rowvec = e.rowvec;
   o->alpha = (e.alpha == 0.f) ? 1.f : e.alpha;
   o->seed = e.seed;
+  o->colsum = e.colsum;
   o->step = step_source();
   o->drop_threshold = 0; o->drop_scale = 1.f;
   MTVAF_REQUIRE(e.mode >= 0 && e.mode <= MTVAF_EPI_ROWSCALE, "bad epilogue mode %d", e.mode);
@@ -46,6 +48,9 @@ inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N
     MTVAF_REQUIRE(e.aux != nullptr, "epilogue mode %d needs aux", e.mode);
   if (e.mode == MTVAF_EPI_SQNORM || e.mode == MTVAF_EPI_ROWSCALE)
     MTVAF_REQUIRE(e.rowvec != nullptr, "epilogue mode %d needs rowvec", e.mode);
+  if (e.colsum)
+    MTVAF_REQUIRE(e.mode != MTVAF_EPI_ATOMIC_F32 && e.mode != MTVAF_EPI_SQNORM && e.out != nullptr,
+                  "epilogue: colsum needs a stored output");
   if (splits > 1)
     MTVAF_REQUIRE(e.mode == MTVAF_EPI_ATOMIC_F32 || (e.mode == MTVAF_EPI_SQNORM && e.out == nullptr),
                   "split-K needs an accumulating epilogue");

@@ -311,6 +311,7 @@ extern "C" int mtvaf_gemm_f32(const void* A, int64_t lda, int a_mn_major, const 
   else
     gemm_f32_kernel<true, false><<<grid, S_THREADS, 0, st>>>(a, lda, b, ldb, M, N, K, k_per, ep, a_vec, b_vec);
   MTVAF_LAUNCH_CHECK();
+  if (epi->colsum) return mtvaf_colsum(epi->out, epi->ldo, epi->out_dtype, M, N, epi->colsum, stream);
   return 0;
 }
 

@@ -60,9 +60,18 @@ extern "C" int mtvaf_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const
   int rc = make_epi_args(*epi, MTVAF_BF16, M, N, splits, &ep);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!a_mn_major && !b_mn_major) return gemm_tc_kk(A, lda, B, ldb, M, N, K, ep, splits, st);
-  if (!a_mn_major && b_mn_major) return gemm_tc_kmn(A, lda, B, ldb, M, N, K, ep, splits, st);
-  if (a_mn_major && b_mn_major) return gemm_tc_mnmn(A, lda, B, ldb, M, N, K, ep, splits, st);
-  MTVAF_REQUIRE(false, "mtvaf_gemm_bf16: A MN-major with B K-major is not used by the path");
-  return -1;
+  // optional column sums of the output: inside the TMA-staged epilogue of the CTA-pair kernel, else a pass over `out`
+  const bool staged_mode = ep.mode == MTVAF_EPI_STORE || ep.mode == MTVAF_EPI_GELU || ep.mode == MTVAF_EPI_TANH ||
+                           ep.mode == MTVAF_EPI_RESID || ep.mode == MTVAF_EPI_MUL_DGELU || ep.mode == MTVAF_EPI_MUL_DTANH;
+  const bool fused = ep.colsum && ep.staged && staged_mode && M >= 256 && gemm_impl_override() == 0;
+  float* post = fused ? nullptr : ep.colsum;
+  if (!fused) ep.colsum = nullptr;
+  if (!a_mn_major && !b_mn_major) rc = gemm_tc_kk(A, lda, B, ldb, M, N, K, ep, splits, st);
+  else if (!a_mn_major && b_mn_major) rc = gemm_tc_kmn(A, lda, B, ldb, M, N, K, ep, splits, st);
+  else if (a_mn_major && b_mn_major) rc = gemm_tc_mnmn(A, lda, B, ldb, M, N, K, ep, splits, st);
+  else {
+    MTVAF_REQUIRE(false, "mtvaf_gemm_bf16: A MN-major with B K-major is not used by the path");
+  }
+  if (rc == 0 && post) rc = mtvaf_colsum(epi->out, epi->ldo, epi->out_dtype, M, N, post, stream);
+  return rc;
 }

@@ -343,6 +343,32 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               }
             }
           }
+          if (ep.colsum) {                           // kernel-uniform
+            // column sums of the box just staged (the bf16 values as stored): lane = column pair, 32 conflict-free
+            // 4-byte reads down the rows.  Rows past M hold epi(0) of zero-filled operand rows: excluded.
+            const int rows_ok = min(32, M - row0);
+            float s0 = 0.f, s1 = 0.f;
+            const uint32_t colb = out_a + ((lane & 3) << 2);
+            const int piece = lane >> 2;
+            // all 32 loads in flight at once (the epilogue is latency-bound here), two partial sums per column
+            uint32_t v[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[rr]) : "r"(colb + rr * 128 + ((piece ^ (rr & 7)) << 4)));
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 2) {
+              const float2 fa = unpack_bf16x2(rr < rows_ok ? v[rr] : 0u);
+              const float2 fb = unpack_bf16x2(rr + 1 < rows_ok ? v[rr + 1] : 0u);
+              s0 += fa.x; s1 += fa.y;
+              t0 += fb.x; t1 += fb.y;
+            }
+            s0 += t0;
+            s1 += t1;
+            const int cc = col0 + 2 * lane;
+            if (cc < N) atomicAdd(ep.colsum + cc, s0);
+            if (cc + 1 < N) atomicAdd(ep.colsum + cc + 1, s1);
+          }
           ++used;
         }
         tc_fence_before();

@@ -330,10 +330,11 @@ class Engine:
                                          f.g(ln("output.LayerNorm.weight")), f.g(ln("output.LayerNorm.bias")),
                                          d_bias=f.g(ln("output.dense.bias")), p_drop=p_h, seed=sd(16 * i + 4))
             ops.linear_wgrad(dd2, s["g"], f.g(ln("output.dense.weight")))
-            dpre = ops.linear_dgrad(dd2, self.cw(ln("output.dense.weight")), mode=L.EPI_MUL_DGELU, aux=s["pre"])
+            # (d(intermediate.dense.bias) = column sums of dpre: summed from the staging boxes of this GEMM's epilogue)
+            dpre = ops.linear_dgrad(dd2, self.cw(ln("output.dense.weight")), mode=L.EPI_MUL_DGELU, aux=s["pre"],
+                                    colsum=f.g(ln("intermediate.dense.bias")))
             # ---- intermediate: g = gelu(a W1^T + b1)
             ops.linear_wgrad(dpre, s["a"], f.g(ln("intermediate.dense.weight")))
-            ops.colsum(dpre, f.g(ln("intermediate.dense.bias")))
             da = ops.linear_dgrad(dpre, self.cw(ln("intermediate.dense.weight")), mode=L.EPI_RESID, aux=dz2)
             # ---- attention output block: a = LN(dropout(ctx Wo^T + bo) + x)
             dz1, dd1 = ops.layernorm_bwd(da, s["z1"], f.w(ln("attention.output.LayerNorm.weight")), s["m1"], s["r1"],

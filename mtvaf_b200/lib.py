@@ -26,7 +26,7 @@ class Epilogue(C.Structure):
     _fields_ = [("mode", C.c_int32), ("out_dtype", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int64),
                 ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("out2", C.c_void_p),
                 ("ld_out2", C.c_int64), ("rowvec", C.c_void_p), ("alpha", C.c_float), ("p_drop", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("colsum", C.c_void_p)]
 
 
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64

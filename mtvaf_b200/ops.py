@@ -62,7 +62,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          mode: int = L.EPI_STORE, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
          bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          out2: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, alpha: float = 1.0,
-         p_drop: float = 0.0, seed: int = 0, splits: int = 1, ldo: Optional[int] = None) -> Optional[torch.Tensor]:
+         p_drop: float = 0.0, seed: int = 0, splits: int = 1, ldo: Optional[int] = None,
+         colsum: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """D[M,N] = epilogue(alpha * A B^T) -- see MtvafEpilogue in the header. a, b are 2-D row-major
     tensors: a is [M,K] (a_mn=False) or [K,M] (a_mn=True); same for b with N."""
     _cuda(a, b, out, bias, aux, out2, rowvec)
@@ -85,6 +86,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     ep.alpha = alpha
     ep.p_drop = p_drop
     ep.seed = seed
+    ep.colsum = _p(colsum)
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() >= N
     if bias is not None:
         assert bias.dtype == torch.float32
     if aux is not None:

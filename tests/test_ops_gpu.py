@@ -83,6 +83,27 @@ def test_gemm_wgrad_layout(ops, Lb, dtype, T, N, K):
     assert rel_err(dw, 2 * ref) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(1000, 3072, 768), (300, 768, 256), (130, 200, 64), (4099, 2304, 768)])
+def test_gemm_fused_column_sums(ops, Lb, dtype, M, N, K):
+    """MtvafEpilogue.colsum: += column sums of the stored output, fused (CTA-pair staged epilogue, M >= 256, bf16) or
+    as a post-pass (every other path); partial last row tile and ragged N included."""
+    dy = rnd(M, K, seed=31, dtype=dtype)
+    w = rnd(K, N, seed=32, scale=0.05, dtype=dtype)
+    aux = rnd(M, N, seed=33, dtype=dtype)
+    base = rnd(N, seed=34)
+    cs = base.clone()
+    out = ops.gemm(dy, w, b_mn=True, M=M, N=N, K=K, mode=Lb.EPI_MUL_DGELU, aux=aux, colsum=cs)
+    ref = out.float().sum(0)
+    assert rel_err(cs - base, ref) < (2e-3 if dtype == torch.bfloat16 else 2e-5)
+    out2 = ops.gemm(dy, w, b_mn=True, M=M, N=N, K=K, mode=Lb.EPI_MUL_DGELU, aux=aux)
+    assert torch.equal(out, out2)
+    cs2 = torch.zeros(N, device=DEV)
+    bias = rnd(N, seed=35)
+    y = ops.linear_fwd(dy, w.t().contiguous(), bias, colsum=cs2)          # STORE + bias: rows past M must not count
+    assert rel_err(cs2, y.float().sum(0)) < (2e-3 if dtype == torch.bfloat16 else 2e-5)
+
+
 def test_gemm_tag_head_shapes_bf16(ops, Lb):
     """The tag head fc 768 -> 11 (models/bert_model.py:510) on the tcgen05 GEMMs in bf16 mode: N = 11 forward with fp32
     emissions, K = 11 data gradient, M = 11 weight gradient from a [T,16] zero-padded d(emissions) operand."""

@@ -34,6 +34,7 @@ def main():
     dkp = torch.zeros(B, nh, P, d, device=dev)
     dvp = torch.zeros(B, nh, P, d, device=dev)
     gam, bet = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+    dbias_i = torch.zeros(4 * H, device=dev)
     dgam, dbet, dbias = torch.zeros(H, device=dev), torch.zeros(H, device=dev), torch.zeros(H, device=dev)
 
     state = {}
@@ -56,6 +57,8 @@ def main():
         ("attn_out_fwd_resid", lambda: ops.linear_fwd(x, w_o, b_h, out=o_h, mode=Lb.EPI_RESID, aux=x, p_drop=0.1, seed=5)),
         ("ffn2_fwd_resid", lambda: ops.linear_fwd(xi, w_2, b_h, out=o_h, mode=Lb.EPI_RESID, aux=x, p_drop=0.1, seed=6)),
         ("ffn2_dgrad_dgelu", lambda: ops.gemm(x, w_2, b_mn=True, M=T, N=4 * H, K=H, out=o_i, mode=Lb.EPI_MUL_DGELU, aux=o_i2)),
+        ("ffn2_dgrad_dgelu_colsum", lambda: ops.gemm(x, w_2, b_mn=True, M=T, N=4 * H, K=H, out=o_i, mode=Lb.EPI_MUL_DGELU,
+                                                     aux=o_i2, colsum=dbias_i)),
         ("ffn1_dgrad_resid", lambda: ops.gemm(xi, w_1, b_mn=True, M=T, N=H, K=4 * H, out=o_h, mode=Lb.EPI_RESID, aux=x)),
         ("attn_out_dgrad_store", lambda: ops.gemm(x, w_o, b_mn=True, M=T, N=H, K=H, out=o_h)),
         ("ffn1_wgrad", lambda: ops.linear_wgrad(xi, x, dw)),
