@@ -206,9 +206,46 @@ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
 __device__ __forceinline__ unsigned long long step_seed(unsigned long long seed, const unsigned long long* step) {
   return step ? seed + (*step) * 0x9E3779B97F4A7C15ull : seed;
 }
-// threshold = round(p * 2^32) (clamped); element is KEPT iff bits >= threshold
+// Hidden-state dropout mask: ONE hash per aligned QUAD of elements (idx >> 2), whose 32 x 64 -> 64-bit product is
+// consumed as four fields (lo, lo << 16, hi, hi << 16), each compared with the full 32-bit threshold
+// threshold = round(p * 2^32): fields 0 / 2 are exact to 2^-32, fields 1 / 3 have 16-bit resolution (|dp| <= 1.6e-5).
+// Element idx is KEPT iff field (idx & 3) of quad (idx >> 2) >= threshold.  ~2.5 integer ops per element instead of
+// 9: the RESID GEMM epilogue and the LayerNorm backward are issue-bound (profiles/r1_ncu_hot_v7.md).
+__device__ __forceinline__ void dropout_quad(uint64_t seed, uint64_t quad, uint32_t (&f)[4]) {
+  const uint32_t lo = static_cast<uint32_t>(quad), hi = static_cast<uint32_t>(quad >> 32);
+  const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t h = (lo ^ s0) * 0x9E3779B1u;
+  h ^= h >> 15;
+  h ^= hi * 0x85EBCA77u + s1;
+  const unsigned long long w = static_cast<unsigned long long>(h) * 0x85EBCA77C2B2AE3Dull;   // IMAD.WIDE + IMAD
+  const uint32_t wl = static_cast<uint32_t>(w), wh = static_cast<uint32_t>(w >> 32);
+  f[0] = wl;
+  f[1] = wl << 16;
+  f[2] = wh;
+  f[3] = wh << 16;
+}
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
-  return dropout_bits(seed, idx) >= threshold;
+  uint32_t f[4];
+  dropout_quad(seed, idx >> 2, f);
+  const uint32_t i = static_cast<uint32_t>(idx) & 3u;
+  return (i == 0 ? f[0] : i == 1 ? f[1] : i == 2 ? f[2] : f[3]) >= threshold;
+}
+// keep bits of the 8 consecutive elements idx0 .. idx0 + 7 (bit j = element idx0 + j)
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t idx0, uint32_t threshold) {
+  uint32_t keep = 0;
+  if ((static_cast<uint32_t>(idx0) & 3u) == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t f[4];
+      dropout_quad(seed, (idx0 >> 2) + q, f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) keep |= (f[j] >= threshold ? 1u : 0u) << (4 * q + j);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep |= (dropout_keep(seed, idx0 + j, threshold) ? 1u : 0u) << j;
+  }
+  return keep;
 }
 
 // ---- attention-probability dropout (modeling_roberta.py:268) -----------------------------------

@@ -161,6 +161,22 @@ __global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = dropout_keep(seed, (unsigned long long)i, thr) ? from_f<T>(to_f<T>(x[i]) * scale) : from_f<T>(0.f);
 }
+// 8 elements per thread and step: 16-byte (bf16) / 2 x 16-byte (fp32) accesses, two mask hashes per vector
+template <typename T>
+__global__ void dropout_apply_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, uint32_t thr,
+                                         float scale, unsigned long long seed_in,
+                                         const unsigned long long* __restrict__ step) {
+  const unsigned long long seed = step_seed(seed_in, step);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    Vec8<T>::load(x + i * 8, v);
+    const uint32_t keep = dropout_keep8(seed, (unsigned long long)i * 8, thr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * scale : 0.f;
+    Vec8<T>::store(y + i * 8, v);
+  }
+}
 template <typename TD, typename TS>
 __global__ void add_inplace_kernel(TD* __restrict__ dst, const TS* __restrict__ src, long long n, float alpha) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -330,7 +346,14 @@ extern "C" int mtvaf_dropout_apply(const void* x, void* y, int64_t n, int dtype,
   double t = (double)p_drop * 4294967296.0;
   const uint32_t thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
   const float scale = 1.f / (1.f - p_drop);
-  if (dtype == MTVAF_BF16)
+  const bool vec = n % 8 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0;
+  if (vec && dtype == MTVAF_BF16)
+    dropout_apply_vec_kernel<__nv_bfloat16><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, thr, scale, seed, step_source());
+  else if (vec)
+    dropout_apply_vec_kernel<float><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (float*)y, n / 8, thr, scale, seed, step_source());
+  else if (dtype == MTVAF_BF16)
     dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, thr, scale, seed, step_source());
   else

@@ -24,19 +24,25 @@ struct StagedEpi {
 };
 
 // dropout keep-mask bits for 32 consecutive elements starting at 64-bit index idx0 (same function as
-// dropout_keep(seed, idx0 + j, thr) of common.cuh, with the seed / high-word terms hoisted out of the loop)
+// dropout_keep(seed, idx0 + j, thr) of common.cuh): eight quads, seed / high-word terms hoisted out of the loop
 __device__ __forceinline__ uint32_t dropout_mask32(unsigned long long seed, unsigned long long idx0, uint32_t thr) {
-  const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
-  const uint32_t lo0 = static_cast<uint32_t>(idx0), hi0 = static_cast<uint32_t>(idx0 >> 32);
   uint32_t keep = 0;
-  if (lo0 <= 0xFFFFFFFFu - 31u) {
-    const uint32_t hterm = hi0 * 0x85EBCA77u + s1;
+  const unsigned long long q0 = idx0 >> 2;
+  if ((static_cast<uint32_t>(idx0) & 3u) == 0 && static_cast<uint32_t>(q0) <= 0xFFFFFFFFu - 7u) {
+    const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+    const uint32_t lo0 = static_cast<uint32_t>(q0);
+    const uint32_t hterm = static_cast<uint32_t>(q0 >> 32) * 0x85EBCA77u + s1;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      uint32_t h = ((lo0 + j) ^ s0) * 0x9E3779B1u;
+    for (int q = 0; q < 8; ++q) {
+      uint32_t h = ((lo0 + q) ^ s0) * 0x9E3779B1u;
       h ^= h >> 15;
-      h = (h ^ hterm) * 0xC2B2AE3Du;
-      keep |= (h >= thr ? 1u : 0u) << j;
+      h ^= hterm;
+      const unsigned long long w = static_cast<unsigned long long>(h) * 0x85EBCA77C2B2AE3Dull;
+      const uint32_t wl = static_cast<uint32_t>(w), wh = static_cast<uint32_t>(w >> 32);
+      keep |= (wl >= thr ? 1u : 0u) << (4 * q);
+      keep |= ((wl << 16) >= thr ? 1u : 0u) << (4 * q + 1);
+      keep |= (wh >= thr ? 1u : 0u) << (4 * q + 2);
+      keep |= ((wh << 16) >= thr ? 1u : 0u) << (4 * q + 3);
     }
   } else {
 #pragma unroll 1

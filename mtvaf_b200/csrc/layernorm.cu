@@ -82,6 +82,85 @@ layernorm_fwd_kernel(const T* __restrict__ z, T* __restrict__ y, const float* __
 // so the separate dropout and column-sum passes over [T,H] disappear.
 // NV = ceil(H / 256) vectors of 8 elements per lane; the next row's loads are issued before the current
 // row's reductions (raw 16-byte vectors held in registers) to keep enough bytes in flight per SM.
+// (A cp.async ring in shared memory with three rows in flight per warp was measured SLOWER, 51.5 vs 45.1 us: the
+// kernel is issue-bound -- 886 warp instructions per row, 56 % issue utilisation -- not latency-bound.)
+// one row of the backward: x / g hold z and dy on entry
+template <typename T, int NV>
+__device__ __forceinline__ void ln_bwd_row(float (&x)[NV][8], float (&g)[NV][8], float mean, float rstd, int row, int H,
+                                           int lane, const float* __restrict__ gamma, T* __restrict__ dz,
+                                           T* __restrict__ dd, bool want_bias, uint32_t drop_thr, float drop_scale,
+                                           unsigned long long seed, float (&ag)[NV][8], float (&ab)[NV][8],
+                                           float (&ac)[NV][8]) {
+  using V = Vec8<T>;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * 8;
+    if (c < H) {
+      float gm[8];
+      Vec8<float>::load(gamma + c, gm);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[v][j] - mean) * rstd;
+        const float d = g[v][j];
+        ag[v][j] += d * xh;
+        ab[v][j] += d;
+        const float gg = d * gm[j];
+        x[v][j] = xh;
+        g[v][j] = gg;
+        s1 += gg;
+        s2 += gg * xh;
+      }
+    }
+  }
+  s1 = warp_sum(s1) / (float)H;
+  s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * 8;
+    if (c < H) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[v][j] - s1 - x[v][j] * s2);
+      V::store(dz + (long long)row * H + c, o);
+      if (drop_thr) {
+        const uint32_t keep = dropout_keep8(seed, (unsigned long long)row * H + c, drop_thr);   // H % 8 == 0
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * drop_scale : 0.f;
+        V::store(dd + (long long)row * H + c, o);
+      }
+      if (want_bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ac[v][j] += o[j];
+      }
+    }
+  }
+}
+
+// reduce the per-warp parameter-gradient partials across the block, then one atomic per column
+template <int NV>
+__device__ __forceinline__ void ln_bwd_flush(float* red, int H, const float (&ag)[NV][8], const float (&ab)[NV][8],
+                                             const float (&ac)[NV][8], float* d_gamma, float* d_beta, float* d_bias) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int pass = 0; pass < (d_bias ? 3 : 2); ++pass) {
+    float* dst = pass == 0 ? d_gamma : pass == 1 ? d_beta : d_bias;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp * 256 + lane * 8 + j] = pass == 0 ? ag[v][j] : pass == 1 ? ab[v][j] : ac[v][j];
+      __syncthreads();
+      for (int i = threadIdx.x; i < 256; i += LN_WARPS * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[w * 256 + i];
+        const int c = v * 256 + i;
+        if (c < H) atomicAdd(dst + c, s);
+      }
+    }
+  }
+}
+
 template <typename T, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32, (NV <= 3 && sizeof(T) == 2) ? 3 : 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ gamma,
@@ -126,69 +205,11 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const fl
         if (c < H) { rz[v] = V::load_raw(z + (long long)nrow * H + c); rg[v] = V::load_raw(dy + (long long)nrow * H + c); }
       }
     }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * 32 + lane) * 8;
-      if (c < H) {
-        float gm[8];
-        Vec8<float>::load(gamma + c, gm);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (x[v][j] - mean) * rstd;
-          const float d = g[v][j];
-          ag[v][j] += d * xh;
-          ab[v][j] += d;
-          const float gg = d * gm[j];
-          x[v][j] = xh;
-          g[v][j] = gg;
-          s1 += gg;
-          s2 += gg * xh;
-        }
-      }
-    }
-    s1 = warp_sum(s1) / (float)H;
-    s2 = warp_sum(s2) / (float)H;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * 32 + lane) * 8;
-      if (c < H) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[v][j] - s1 - x[v][j] * s2);
-        V::store(dz + (long long)row * H + c, o);
-        if (drop_thr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = dropout_keep(seed, (unsigned long long)row * H + c + j, drop_thr) ? o[j] * drop_scale : 0.f;
-          V::store(dd + (long long)row * H + c, o);
-        }
-        if (d_bias) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ac[v][j] += o[j];
-        }
-      }
-    }
+    ln_bwd_row<T, NV>(x, g, mean, rstd, row, H, lane, gamma, dz, dd, d_bias != nullptr, drop_thr, drop_scale, seed, ag, ab, ac);
   }
-  // reduce the per-warp parameter-gradient partials across the block, then one atomic per column
-  for (int pass = 0; pass < (d_bias ? 3 : 2); ++pass) {
-    float* dst = pass == 0 ? d_gamma : pass == 1 ? d_beta : d_bias;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp * 256 + lane * 8 + j] = pass == 0 ? ag[v][j] : pass == 1 ? ab[v][j] : ac[v][j];
-      __syncthreads();
-      for (int i = threadIdx.x; i < 256; i += LN_WARPS * 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) s += red[w * 256 + i];
-        const int c = v * 256 + i;
-        if (c < H) atomicAdd(dst + c, s);
-      }
-    }
-  }
+  ln_bwd_flush<NV>(red, H, ag, ab, ac, d_gamma, d_beta, d_bias);
 }
+
 
 // ------------------------------------------------------------------ position ids (bit-exact int64)
 // roberta: mask = ids != pad; pos = cumsum(mask) * mask + pad   (modeling_roberta.py:1717-1719)
