@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mtvaf_b200", choices=["mtvaf_b200", "reference"])
-    ap.add_argument("--per-gpu-batch", type=int, default=int(os.environ.get("MTVAF_BENCH_BATCH", 256)))
+    ap.add_argument("--per-gpu-batch", type=int, default=int(os.environ.get("MTVAF_BENCH_BATCH", 512)),
+                    help="samples per GPU and step (weak scaling); SURVEY.md 8(d) sweeps {16, 64, 256, 512}")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
@@ -319,8 +320,9 @@ def main():
     # profiler here); null when the capture is for another batch size
     traffic, traffic_src = None, None
     try:
-        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if "gemm_traffic" in f and f.endswith(".json"))
-        if cands and B == 256 and args.dtype == "bf16":
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles"))
+                       if "gemm_traffic" in f and f.endswith("_b%d.json" % B))
+        if cands and args.dtype == "bf16":
             tj = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
             traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/" + cands[-1]
     except Exception:
