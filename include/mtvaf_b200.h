@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MTVAF_ABI_VERSION 1
+#define MTVAF_ABI_VERSION 2   /* 2: MtvafEpilogue.colsum, mtvaf_attention_bwd_ex, mtvaf_set_sm_reserve */
 #define MTVAF_F32 0
 #define MTVAF_BF16 1
 

@@ -25,7 +25,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         if n not in ("mtvaf_last_error", "mtvaf_launch_count"):
             assert n in lib.SIGNATURES, n
-    assert lib.abi_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "mtvaf_b200.h")).read()
+    assert lib.abi_version() == int(re.search(r"#define MTVAF_ABI_VERSION (\d+)", hdr).group(1)) == 2
+    # the ctypes mirror of MtvafEpilogue must have the header's fields, in order
+    body = re.search(r"typedef struct MtvafEpilogue \{(.*?)\} MtvafEpilogue;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(\w+)\s*;", body)
+    assert fields == [f[0] for f in lib.Epilogue._fields_], (fields, lib.Epilogue._fields_)
 
 
 def test_no_cpu_fallback_in_product_package():
