@@ -5,7 +5,7 @@
 //   TMA  : Q tile, the visual-prefix K_p/V_p rows (8-row boxes) and the text K/V rows (64-row boxes)
 //          land in SWIZZLE_128B shared memory -- the torch.cat of models/modeling_roberta.py:221-222 is
 //          just two groups of TMA boxes into one key-row numbering (prefix padded to a multiple of 8);
-//          the next item's loads are issued as soon as this item's second MMA has retired
+//          the next item's Q / K loads are issued as soon as S has retired, its V load as soon as O has retired
 //   MMA 1: S[q, key] = Q K^T  (tcgen05.mma, both operands K-major)            -> TMEM columns [0, N16)
 //   SIMT : thread = (query row == TMEM lane, every other 8-key unit): 1/sqrt(d) and the additive key mask
 //          (-10000.0, models/modeling_roberta.py:1000) folded into one FFMA in the log2 domain, row max and
@@ -46,8 +46,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sP = sV + key_rows * 128;                 // n_chunks x [128][64] bf16
   float* sMask = reinterpret_cast<float*>(sP + n_chunks * 16384);     // [N16], additive mask * log2(e)
   float* sExch = sMask + ((a.N16 + 15) / 16) * 16;   // [2][2][128]: partial row max / row sum per column half
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 512);          // load, s, o
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 512);          // Q+K landed, s, o, V landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;       // TMEM lane group / which half of the units
@@ -59,7 +59,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (tid == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmKV);
     if (a.P8 > 0) { prefetch_tmap(&tmKp); prefetch_tmap(&tmVp); }
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
     fence_barrier_init();
   }
   __syncwarp();                                      // tcgen05.alloc is .sync.aligned: reconverge warp 0 first
@@ -69,22 +69,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  auto issue_loads = [&](int item) {                 // one thread
+  // Q and K are free again as soon as S = Q K^T has retired, V only after O = P V: two barriers, so the next item's
+  // Q / K tiles travel during this item's softmax and its S MMA can start the moment the item begins
+  auto issue_qk = [&](int item) {                    // one thread
     const int qt = item % q_tiles, bh = item / q_tiles;
     const int b = bh / a.nh, h = bh - b * a.nh;
-    const uint32_t bytes = 16384u + 2u * key_rows * 128u;
-    mbar_arrive_expect_tx(&bars[0], bytes);
+    mbar_arrive_expect_tx(&bars[0], 16384u + (uint32_t)key_rows * 128u);
     tma_load_2d(sQ, &tmQ, &bars[0], h * 64, b * a.L + qt * 128);
-    for (int r = 0; r < a.P8; r += 8) {
-      tma_load_2d(sK + r * 128, &tmKp, &bars[0], 0, (b * a.nh + h) * a.P + r);
-      tma_load_2d(sV + r * 128, &tmVp, &bars[0], 0, (b * a.nh + h) * a.P + r);
-    }
-    for (int r = 0; r < a.L64; r += 64) {
-      tma_load_2d(sK + (a.P8 + r) * 128, &tmKV, &bars[0], H + h * 64, b * a.L + r);
-      tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, &bars[0], 2 * H + h * 64, b * a.L + r);
-    }
+    for (int r = 0; r < a.P8; r += 8) tma_load_2d(sK + r * 128, &tmKp, &bars[0], 0, (b * a.nh + h) * a.P + r);
+    for (int r = 0; r < a.L64; r += 64) tma_load_2d(sK + (a.P8 + r) * 128, &tmKV, &bars[0], H + h * 64, b * a.L + r);
   };
-  if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
+  auto issue_v = [&](int item) {                     // one thread
+    const int bh = item / q_tiles;
+    const int b = bh / a.nh, h = bh - b * a.nh;
+    mbar_arrive_expect_tx(&bars[3], (uint32_t)key_rows * 128u);
+    for (int r = 0; r < a.P8; r += 8) tma_load_2d(sV + r * 128, &tmVp, &bars[3], 0, (b * a.nh + h) * a.P + r);
+    for (int r = 0; r < a.L64; r += 64) tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, &bars[3], 2 * H + h * 64, b * a.L + r);
+  };
+  if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
 
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const float sc2 = a.scale * kFwdLog2e;             // fold log2(e): exp(x) = exp2(x * log2e)
@@ -92,20 +94,33 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
   const int units = a.N16 >> 3;
 
+  // key `k` of batch row `b` -> additive mask; keys >= N16 are never read (N16 <= 448 < 2 * kFwdThreads)
+  auto fetch_mask = [&](int b, int k) -> float {
+    if (k >= a.N16) return 0.f;
+    if (k < a.P8) return (k < a.P) ? 0.f : -INFINITY;
+    const int t = k - a.P8;
+    return (t < a.L) ? (a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kFwdLog2e) : -INFINITY;
+  };
+  float mask_next[2] = {0.f, 0.f};
+  if ((int)blockIdx.x < n_items) {
+    const int b0 = (int)blockIdx.x / q_tiles / a.nh;
+    mask_next[0] = fetch_mask(b0, tid);
+    mask_next[1] = fetch_mask(b0, tid + kFwdThreads);
+  }
+
   uint32_t ph = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ph ^= 1) {
     const int qt = item % q_tiles, bh = item / q_tiles;
     const int b = bh / a.nh, h = bh - b * a.nh;
     const int q = qt * 128 + row;
-    // additive key mask (x log2 e) in smem-key numbering: prefix rows [0,P) visible, [P,P8) padding, text rows follow
-    for (int k = tid; k < a.N16; k += kFwdThreads) {
-      float m;
-      if (k < a.P8) m = (k < a.P) ? 0.f : -INFINITY;
-      else {
-        const int t = k - a.P8;
-        m = (t < a.L) ? (a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kFwdLog2e) : -INFINITY;
-      }
-      sMask[k] = m;
+    // additive key mask (x log2 e) in smem-key numbering: prefix rows [0,P) visible, [P,P8) padding, text rows follow.
+    // The values were fetched one item ahead (mask_next): the global load no longer sits in front of the barrier.
+    if (tid < a.N16) sMask[tid] = mask_next[0];
+    if (tid + kFwdThreads < a.N16) sMask[tid + kFwdThreads] = mask_next[1];
+    if (item + (int)gridDim.x < n_items) {
+      const int bn = (item + (int)gridDim.x) / q_tiles / a.nh;
+      mask_next[0] = fetch_mask(bn, tid);
+      mask_next[1] = fetch_mask(bn, tid + kFwdThreads);
     }
     if (tid == 0) {
       mbar_wait(&bars[0], ph);
@@ -126,6 +141,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&bars[1], ph);
     __syncwarp();
     tc_fence_after();
+    if (tid == 0 && item + (int)gridDim.x < n_items) issue_qk(item + gridDim.x);   // S retired: Q / K are free
+    __syncwarp();
 
     // ---- pass 1: row max of (S / sqrt(d) + mask) * log2 e over this thread's units
     float mx = -INFINITY;
@@ -179,6 +196,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     if (tid == 0) {
       // ---- O = P V
+      mbar_wait(&bars[3], ph);                         // V landed (long ago: requested when the previous O retired)
+      tc_fence_after();
       const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
       const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
       const int ksteps = a.N16 / 16;
@@ -192,8 +211,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&bars[2], ph);
     __syncwarp();
     tc_fence_after();
-    // Q / K / V / P of this item are consumed: fetch the next item's tiles behind the epilogue
-    if (tid == 0 && item + (int)gridDim.x < n_items) issue_loads(item + gridDim.x);
+    // V / P of this item are consumed: fetch the next item's V behind the epilogue
+    if (tid == 0 && item + (int)gridDim.x < n_items) issue_v(item + gridDim.x);
     __syncwarp();
 
     // tcgen05.ld is warp-collective (.sync.aligned): EVERY lane issues the loads (rows past L included,
