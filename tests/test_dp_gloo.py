@@ -95,6 +95,63 @@ def _worker_owned(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_embeddings(rank, world, port, q):
+    """The embedding tables (packed last in the flat buffer) are reduced from `tail_grad_hook`, inside backward; the
+    tail pass at the end must then skip them (no double averaging) and the flag must reset for the next step."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mtvaf_b200.optim import GradSync
+        layer_ranges = [(0, 1024), (1024, 2048)]
+        total = 8192
+        names = ["bert.encoder.layer.0.w", "bert.encoder.layer.1.w", "fc.weight", "bert.embeddings.word_embeddings.weight",
+                 "bert.embeddings.LayerNorm.weight"]
+        offsets = {names[0]: (0, 1024), names[1]: (1024, 1024), names[2]: (2048, 512), names[3]: (4096, 4000),
+                   names[4]: (8128, 64)}
+        for step in range(2):
+            eng = _fake_engine(total, layer_ranges, rank)
+            eng.flat.names, eng.flat.offsets = names, offsets
+            expect = sum(_fake_engine(total, layer_ranges, r).flat.G for r in range(world)) / world
+            if step == 0:
+                sync = GradSync(eng)
+                assert sync._emb_lo == 4096 and eng.tail_grad_hook is not None
+            else:                                               # same GradSync object, fresh gradients
+                sync.engine.flat.G.copy_(eng.flat.G)
+                eng = sync.engine
+            eng.layer_grad_hook(1)
+            eng.layer_grad_hook(0)
+            eng.tail_grad_hook()                                 # embedding backward done
+            assert sync.tail_ranges() == [(2048, 4096)]          # embeddings no longer part of the tail
+            eng.tail_grad_hook()                                 # idempotent within a step
+            sync.launch_tail()
+            sync.wait_layers()
+            sync.wait_tail()
+            assert torch.allclose(eng.flat.G, expect, atol=1e-6), "step %d" % step
+            assert sync.tail_ranges() == [(2048, total)]         # flag reset: next step reduces them again
+        q.put((rank, "ok"))
+    except Exception as e:                                       # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradsync_embedding_hook_world2_gloo():
+    from mtvaf_b200 import build
+    build.build()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_embeddings, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
 def test_gradsync_optimizer_owned_ranges_world2_gloo():
     from mtvaf_b200 import build
     build.build()
