@@ -43,6 +43,8 @@ def main():
         state["ctx"], state["lse"], _ = ops.attention_fwd(o_qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.1, seed=3)
 
     def attn_b():
+        if "ctx" not in state:              # ONLY=attn_bwd: the backward needs the forward's outputs
+            attn_f()
         ops.attention_bwd(x, o_qkv, kp, vp, key_mask, state["ctx"], state["lse"], B, Lq, nh, d, dkp=dkp, dvp=dvp,
                           p_drop=0.1, seed=3)
 
