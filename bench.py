@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true",
                     help="issue every launch from Python each step instead of replaying the whole-step CUDA graph")
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    ap.add_argument("--deadline-s", type=float, default=float(os.environ.get("MTVAF_BENCH_DEADLINE_S", 1200)),
+                    help="hard wall-clock limit: a hung collective must not outlive the round (exit code 3, no JSON line)")
     return ap.parse_args()
 
 
@@ -153,6 +155,14 @@ def run_reference(args, rank, world, emit):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.deadline_s > 0:
+        def _deadline():
+            sys.stderr.write("bench.py: exceeded --deadline-s %.0f s (hung collective or device?) -- aborting\n" % args.deadline_s)
+            sys.stderr.flush()
+            os._exit(3)
+        _t = threading.Timer(args.deadline_s, _deadline)
+        _t.daemon = True
+        _t.start()
     # the contract is ONE JSON line on stdout: libraries (NCCL's version banner) write there too, so everything
     # before the final print goes to stderr
     real_stdout = os.dup(1)
