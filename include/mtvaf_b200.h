@@ -170,7 +170,9 @@ int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* kp, const v
                         const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx, float* lse,
                         float* probs, int dtype, float p_drop, uint64_t seed, void* stream);
 /* 0 (default) = tcgen05 kernels whenever dtype is bf16 and the shape fits (P+L <= 448 fwd), SIMT otherwise;
- * 1 = SIMT kernels only, 2 = tcgen05 kernels but the generic (non-pipelined) backward (A/B testing). */
+ * 1 = SIMT kernels only, 2 = tcgen05 kernels but the generic (non-pipelined) backward (A/B testing),
+ * 3 = 2 plus the EXPERIMENTAL tcgen05 backward for 128 < L <= 256 (attention_tc_bwd_long.cu; not yet validated on
+ *     hardware, never selected by default). */
 int mtvaf_set_attention_impl(int impl);
 /* dqkv: [B*L, 3*nh*d]; dkp/dvp: [B, nh, P, d] fp32 gradient of the prefix (may be NULL);
  * dsum_scratch: [B, nh, L] fp32 workspace (rowsum(dO * O)). */

@@ -482,7 +482,8 @@ using namespace mtvaf;
 static int g_attention_impl = 0;
 namespace mtvaf { int attention_impl_override() { return g_attention_impl; } }
 extern "C" int mtvaf_set_attention_impl(int impl) {
-  MTVAF_REQUIRE(impl >= 0 && impl <= 2, "attention impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05, generic backward)");
+  MTVAF_REQUIRE(impl >= 0 && impl <= 3,
+                "attention impl must be 0 (auto), 1 (SIMT), 2 (tcgen05, generic backward) or 3 (2 + experimental long-text backward)");
   g_attention_impl = impl;
   return 0;
 }
@@ -547,6 +548,10 @@ extern "C" int mtvaf_attention_bwd_ex(const void* dctx, int64_t ld_dctx, const v
       return attn_bwd_pipe_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, d_bias_qkv, st);
     if (ok && attn_bwd_tc_supported(ta)) {
       if (int rc = attn_bwd_tc_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st)) return rc;
+      return d_bias_qkv ? mtvaf_colsum(dqkv, ld_dqkv, dtype, B * L, 3 * nh * d, d_bias_qkv, stream) : 0;
+    }
+    if (ok && attention_impl_override() == 3 && attn_bwd_long_supported(ta)) {      // experimental, opt-in only
+      if (int rc = attn_bwd_long_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st)) return rc;
       return d_bias_qkv ? mtvaf_colsum(dqkv, ld_dqkv, dtype, B * L, 3 * nh * d, d_bias_qkv, stream) : 0;
     }
   }

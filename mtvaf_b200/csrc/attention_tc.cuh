@@ -39,6 +39,11 @@ bool attn_bwd_pipe_supported(const AttnTcArgs& a);
 int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                          int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
                          float* dbias, cudaStream_t st);
+// EXPERIMENTAL long-text backward (128 < L <= 256), attention_tc_bwd_long.cu: selected only by impl override 3
+bool attn_bwd_long_supported(const AttnTcArgs& a);
+int attn_bwd_long_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
+                         int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
+                         cudaStream_t st);
 int attention_impl_override();   // 0 = auto (tcgen05 when the shape fits), 1 = SIMT only, 2 = tcgen05 without the pipelined bwd
 
 }  // namespace mtvaf

@@ -323,7 +323,8 @@ def embed_ln_bwd(dout, ids, tts, pids, word, pos, typ, gamma, mean, rstd, kind, 
 def set_attention_impl(impl: str):
     """'auto' (tcgen05 kernels when bf16 and the shape fits), 'simt', or 'tc_generic' (tcgen05 kernels with the
     generic instead of the software-pipelined backward) -- A/B testing."""
-    _check(_raw.mtvaf_set_attention_impl({"auto": 0, "simt": 1, "tc_generic": 2}[impl]), "set_attention_impl")
+    _check(_raw.mtvaf_set_attention_impl({"auto": 0, "simt": 1, "tc_generic": 2, "tc_long_experimental": 3}[impl]),
+           "set_attention_impl")
 
 
 def attention_fwd(qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.0, seed=0, want_probs=False):
