@@ -213,16 +213,18 @@ def main():
             except Exception:
                 tail_group = None
 
-    from oracle.make_golden import hf_config          # config helper only (no oracle arithmetic)
-    from oracle import mtvaf_oracle as O
+    from transformers import RobertaConfig               # the product arm never imports oracle/
     from mtvaf_b200 import synthetic as S, ops
     from mtvaf_b200.modules import TVNetSAModel2, FeatureStub
     from mtvaf_b200.optim import FlatAdamW, GradSync
 
     B = args.per_gpu_batch
-    cfg = O.EncoderCfg.roberta_base()
+    # roberta-base (models/bert_model.py:425-429 loads it by name; no network here: random init of that architecture)
+    hf_cfg = RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                           intermediate_size=3072, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5,
+                           pad_token_id=1, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
     torch.manual_seed(1234)                              # identical init on every rank
-    model = TVNetSAModel2(list(range(10)), None, model_args(args.dtype), config=hf_config(cfg),
+    model = TVNetSAModel2(list(range(10)), None, model_args(args.dtype), config=hf_cfg,
                           image_model=FeatureStub()).to(dev)
     model.train()
     eng = model.engine()

@@ -42,3 +42,16 @@ def test_product_arm_needs_cuda():
     r = _run("--steps", "1", "--warmup", "1", timeout=300)
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_product_arm_never_imports_the_oracle():
+    """Only the cpu_baseline / --impl reference leg (cpu_reference_run) may touch oracle/."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn) if (isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle")
+                or (isinstance(n, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in n.names))]
+        if uses:
+            assert fn.name == "cpu_reference_run", fn.name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any((getattr(n, "module", "") or "").startswith("oracle") for n in top)
