@@ -28,6 +28,7 @@ CASES = {
     "encoder_roberta_p36": dict(kind="roberta", B=2, L=48, shape="twitter2017", batch_seed=12, param_seed=102, P=36),
     "encoder_bert": dict(kind="bert", B=2, L=40, shape="twitter2015", batch_seed=13, param_seed=103),
     "tvnet_span_roberta": dict(kind="roberta", B=4, L=32, shape="twitter2015", batch_seed=14, param_seed=104, M=6),
+    "tvnet2_bert": dict(kind="bert", B=3, L=24, shape="twitter2017", batch_seed=15, param_seed=105),
 }
 
 
@@ -61,7 +62,8 @@ def gen_tvnet2(name, c):
     ocfg = ocfg_for(c["kind"])
     params = S.init_params(ocfg, seed=c["param_seed"], ln_jitter=0.05)
     batch = S.make_batch(c["B"], c["L"], vocab=ocfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
-    args = ref_shim.make_args()
+    # the reference picks the backbone by name: "roberta" in args.bert_name (models/bert_model.py:425-429)
+    args = ref_shim.make_args(**({"bert_name": "bert-base-uncased"} if c["kind"] == "bert" else {}))
     model = ref_shim.build_reference_tvnet2(hf_config(ocfg), args, list(range(10)))
     missing = model.load_state_dict(params, strict=False)
     assert not missing.unexpected_keys, missing
@@ -215,6 +217,7 @@ def main():
     gen_encoder("encoder_roberta_p36", CASES["encoder_roberta_p36"])
     gen_encoder("encoder_bert", CASES["encoder_bert"])
     gen_tvnet2("tvnet2_roberta", CASES["tvnet2_roberta"])
+    gen_tvnet2("tvnet2_bert", CASES["tvnet2_bert"])
     gen_tvnet_span("tvnet_span_roberta", CASES["tvnet_span_roberta"])
 
 

@@ -90,6 +90,28 @@ def test_tvnet2_fp32_matches_reference_golden(golden_dir):
     check_fp(fp, g["grad_fp"], 2e-3)
 
 
+@pytest.mark.skipif(os.environ.get("MTVAF_EXPERIMENTAL") != "1",
+                    reason="golden added at the end of round 1 with no GPU time left to run this test once: opt-in "
+                           "(MTVAF_EXPERIMENTAL=1) until it has passed on hardware; the oracle side is checked on CPU")
+def test_tvnet2_bert_backbone_fp32_matches_reference_golden(golden_dir):
+    g = _gold(golden_dir, "tvnet2_bert")
+    c = CASES["tvnet2_bert"]
+    cfg = ocfg_for(c["kind"])
+    params = S.init_params(cfg, seed=c["param_seed"], ln_jitter=0.05)
+    batch = S.make_batch(c["B"], c["L"], vocab=cfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    m = build_tvnet2(cfg, params, "fp32", bert_name="bert-base-uncased")
+    m.eval()
+    out, prob_loss, img_loss = m(**to_dev(batch))
+    assert rel(out.loss, g["loss"]) < 1e-4
+    assert rel(prob_loss, g["prob_loss"]) < 1e-4
+    assert rel(img_loss, g["img_loss"]) < 1e-4
+    assert rel(m.last_emissions, g["emissions"]) < 1e-4
+    assert out.logits == g["logits"]
+    out.loss.backward()
+    fp = grad_fingerprint([(k, None if p.grad is None else p.grad.cpu()) for k, p in m.named_parameters()])
+    check_fp(fp, g["grad_fp"], 2e-3)
+
+
 @pytest.mark.parametrize("name", ["encoder_roberta_p36", "encoder_bert"])
 def test_encoder_fp32_matches_reference_golden(golden_dir, name):
     from mtvaf_b200.modules import RobertaModel, BertModel

@@ -106,6 +106,27 @@ def test_tvnet2_matches_reference_golden(golden_dir):
     _check_fp(fp, g["grad_fp"], 5e-4)
 
 
+def test_tvnet2_bert_backbone_matches_reference_golden(golden_dir):
+    """The BERT branch of TVNetSAModel2 (models/bert_model.py:425-429 picks the backbone by name; token-type
+    embeddings, eps 1e-12, absolute positions 0..L-1): oracle vs the unmodified reference."""
+    g = _load(golden_dir, "tvnet2_bert")
+    c = CASES["tvnet2_bert"]
+    cfg = ocfg_for(c["kind"])
+    params = S.init_params(cfg, seed=c["param_seed"], ln_jitter=0.05)
+    params = {k: v.requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    batch = S.make_batch(c["B"], c["L"], vocab=cfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    o = O.tvnet2_forward(params, cfg, batch, alpha=0.1, beta=0.5)
+    _close(o["loss"], g["loss"], rtol=1e-5, atol=1e-5)
+    _close(o["prob_loss"], g["prob_loss"], rtol=1e-5, atol=1e-3)
+    _close(o["img_loss"], g["img_loss"], rtol=1e-5, atol=1e-6)
+    assert o["logits"] == g["logits"]
+    _close(o["emissions"], g["emissions"])
+    assert torch.equal(o["pseudo_labels"], g["pseudo_labels"])
+    o["loss"].backward()
+    fp = grad_fingerprint([(k, v.grad) for k, v in params.items()])
+    _check_fp(fp, g["grad_fp"], 5e-4)
+
+
 def test_tvnet_span_matches_reference_golden(golden_dir):
     """Span variant TVNetSAModel: oracle restatement vs the unmodified reference."""
     g = _load(golden_dir, "tvnet_span_roberta")
