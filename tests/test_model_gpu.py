@@ -90,10 +90,8 @@ def test_tvnet2_fp32_matches_reference_golden(golden_dir):
     check_fp(fp, g["grad_fp"], 2e-3)
 
 
-@pytest.mark.skipif(os.environ.get("MTVAF_EXPERIMENTAL") != "1",
-                    reason="golden added at the end of round 1 with no GPU time left to run this test once: opt-in "
-                           "(MTVAF_EXPERIMENTAL=1) until it has passed on hardware; the oracle side is checked on CPU")
 def test_tvnet2_bert_backbone_fp32_matches_reference_golden(golden_dir):
+    """BERT branch of TVNetSAModel2 (models/bert_model.py:425-429) against the unmodified reference."""
     g = _gold(golden_dir, "tvnet2_bert")
     c = CASES["tvnet2_bert"]
     cfg = ocfg_for(c["kind"])
