@@ -110,6 +110,37 @@ def test_tvnet2_bert_backbone_fp32_matches_reference_golden(golden_dir):
     check_fp(fp, g["grad_fp"], 2e-3)
 
 
+@pytest.mark.skipif(os.environ.get("MTVAF_EXPERIMENTAL") != "1",
+                    reason="golden added at the end of round 1 with no GPU time left to run this test once: opt-in "
+                           "(MTVAF_EXPERIMENTAL=1) until it has passed on hardware; the oracle side is checked on CPU "
+                           "and test_tvnet2_no_prefix_no_probe_fp32 covers the product against the oracle")
+@pytest.mark.parametrize("variant", ["noauxloss", "no_vao", "no_probe", "no_prefix"])
+def test_tvnet2_flag_variants_fp32_match_reference_golden(golden_dir, variant):
+    gold = _gold(golden_dir, "tvnet2_variants")
+    c, g = gold["case"], gold["variants"][variant]
+    cfg = O.EncoderCfg.roberta_base(vocab_size=c["vocab"])
+    params = S.init_params(cfg, seed=c["param_seed"], ln_jitter=0.05)
+    batch = S.make_batch(c["B"], c["L"], vocab=cfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    flags = dict(g["flags"])
+    m = build_tvnet2(cfg, params, "fp32", **flags)
+    m.eval()
+    b = to_dev(batch)
+    if not flags.get("use_prefix", True):
+        b = {k: v for k, v in b.items() if k in ("input_ids", "attention_mask", "token_type_ids", "labels")}
+    ret = m(**b)
+    assert isinstance(ret, tuple) == g["returns_tuple"]
+    out = ret[0] if isinstance(ret, tuple) else ret
+    assert rel(out.loss, g["loss"]) < 1e-4
+    assert out.logits == g["logits"]
+    if isinstance(ret, tuple):
+        assert rel(ret[1], g["prob_loss"]) < 1e-4
+        if float(g["img_loss"]) != 0.0:
+            assert rel(ret[2], g["img_loss"]) < 1e-4
+    out.loss.backward()
+    fp = grad_fingerprint([(k, None if p.grad is None else p.grad.cpu()) for k, p in m.named_parameters()])
+    check_fp(fp, g["grad_fp"], 2e-3)
+
+
 @pytest.mark.parametrize("name", ["encoder_roberta_p36", "encoder_bert"])
 def test_encoder_fp32_matches_reference_golden(golden_dir, name):
     from mtvaf_b200.modules import RobertaModel, BertModel

@@ -127,6 +127,28 @@ def test_tvnet2_bert_backbone_matches_reference_golden(golden_dir):
     _check_fp(fp, g["grad_fp"], 5e-4)
 
 
+@pytest.mark.parametrize("variant", ["noauxloss", "no_vao", "no_probe", "no_prefix"])
+def test_tvnet2_flag_variants_match_reference_golden(golden_dir, variant):
+    """The flag branches of TVNetSAModel2.forward (noauxloss :489, vao :549-563, use_probe :527-532, use_prefix :486-492)
+    through the unmodified reference (oracle/make_variant_golden.py) vs the oracle."""
+    gold = _load(golden_dir, "tvnet2_variants")
+    c, g = gold["case"], gold["variants"][variant]
+    cfg = O.EncoderCfg.roberta_base(vocab_size=c["vocab"])
+    params = S.init_params(cfg, seed=c["param_seed"], ln_jitter=0.05)
+    params = {k: v.requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    batch = S.make_batch(c["B"], c["L"], vocab=cfg.vocab_size, shape=c["shape"], seed=c["batch_seed"])
+    o = O.tvnet2_forward(params, cfg, batch, alpha=0.1, beta=0.5, **g["flags"])
+    _close(o["loss"], g["loss"], rtol=1e-5, atol=1e-5)
+    assert o["logits"] == g["logits"]
+    if g["prob_loss"] is not None:
+        _close(o["prob_loss"], g["prob_loss"], rtol=1e-5, atol=1e-3)
+    if g["img_loss"] is not None:
+        _close(o["img_loss"], g["img_loss"], rtol=1e-5, atol=1e-6)
+    o["loss"].backward()
+    fp = grad_fingerprint([(k, v.grad) for k, v in params.items()])
+    _check_fp(fp, g["grad_fp"], 5e-4)
+
+
 def test_tvnet_span_matches_reference_golden(golden_dir):
     """Span variant TVNetSAModel: oracle restatement vs the unmodified reference."""
     g = _load(golden_dir, "tvnet_span_roberta")
