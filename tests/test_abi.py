@@ -52,3 +52,28 @@ def test_bad_arguments_return_error_not_crash():
     assert rc == -1 and "null" in lib.last_error()
     rc = lib.raw().mtvaf_probe_labels(None, None, 0, 0, None)
     assert rc == -1
+
+
+def test_header_is_valid_c99_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/mtvaf_b200.h must compile as plain C (and C++), and a C host must link against
+    the shared library and read the ABI version (no compute: no GPU needed)."""
+    import subprocess
+    from mtvaf_b200 import build
+    lib_path = build.build()
+    src = tmp_path / "host.c"
+    src.write_text('#include "mtvaf_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { MtvafEpilogue e; e.mode = MTVAF_EPI_STORE; e.colsum = 0; (void)e;\n'
+                   '  printf("%d %d\\n", mtvaf_abi_version(), MTVAF_ABI_VERSION); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++17")):
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", inc] +
+                           (["-x", "c++"] if cc == "g++" else []) + [str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    exe = tmp_path / "host"
+    r = subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), lib_path,
+                        "-Wl,-rpath," + os.path.dirname(lib_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = r.stdout.split()
+    assert a == b == "2"
