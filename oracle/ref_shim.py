@@ -16,7 +16,20 @@ from types import SimpleNamespace
 import torch
 from torch import nn
 
-REF_ROOT = os.environ.get("MTVAF_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_ref_root() -> str:
+    """MTVAF_REF, else the authoring container's /root/reference, else the byte-for-byte copy staged by
+    oracle/make_ref.py under oracle/_ref (git-ignored; travels to the GPU box)."""
+    cands = [os.environ.get("MTVAF_REF"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "models")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_ref_root()
 
 
 def reference_available() -> bool:
@@ -113,6 +126,13 @@ def _install_stub_modules():
                 __import__(name)
             except Exception:
                 sys.modules[name] = types.ModuleType(name)
+    sm = sys.modules["seqeval.metrics"]
+    if not hasattr(sm, "classification_report"):
+        # only called at epoch end by the trainers (modules/train.py:664); the trainer tests drive `_step` directly
+        def classification_report(*a, **k):
+            raise NotImplementedError("seqeval is not installed (stub)")
+        sm.classification_report = classification_report
+        sys.modules["seqeval"].metrics = sm
 
 
 _REF = None
@@ -145,6 +165,14 @@ def load_reference():
     _REF = SimpleNamespace(bert_model=ref_models, roberta=ref_roberta, bert=ref_bert, probe=ref_probe,
                            label=ref_label, probe_model=ref_probe_model, loss=ref_loss)
     return _REF
+
+
+def load_reference_trainer():
+    """modules/train.py of the unmodified reference (SATrainer / SATrainer2: `_step`, `multiModal_before_train`, the
+    index-walking checkpoint loaders)."""
+    load_reference()
+    import importlib
+    return importlib.import_module("modules.train")
 
 
 def make_args(**over):

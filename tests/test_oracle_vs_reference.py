@@ -49,3 +49,11 @@ def test_construct_label_live_reference():
     x[0, 3] = x[0, 40]
     ref = R.label.ConstructLabelGaget(None)(x)
     assert torch.equal(O.construct_label(x), ref)
+
+
+@pytest.mark.gpu
+def test_oracle_vs_staged_reference_on_the_gpu_box():
+    """The same live comparison on the GPU box, against the copy staged by oracle/make_ref.py (oracle/_ref travels
+    with the gpurun snapshot; /root/reference does not exist there)."""
+    test_tvnet2_live_reference_forward_backward()
+    test_construct_label_live_reference()
