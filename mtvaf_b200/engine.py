@@ -200,7 +200,16 @@ class Engine:
         self.flat = FlatParams(module, enc_prefix, cfg.n_layers)
         self.compute_dtype = compute_dtype
         self.step_counter = 0
-        self.base_seed = 0x5EED
+        # dropout streams follow torch.manual_seed and differ per data-parallel rank (masks are counter-based hashes
+        # of (base_seed, step, site, element): nothing else distinguishes two ranks or two runs)
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:
+            rank = 0
+        self.base_seed = ((torch.initial_seed() ^ 0x5EED) + 7919 * rank) & 0x7FFFFFFF
         self.layer_grad_hook: Optional[Callable[[int], None]] = None   # DP: called when layer i's grads are final
         self.tail_grad_hook: Optional[Callable[[], None]] = None       # DP: called when the embedding grads are final
 
@@ -216,6 +225,12 @@ class Engine:
         self.flat.ensure(dev)
         if self.bf16:
             self.flat.refresh_bf16()
+
+    def new_step(self):
+        """Advance the dropout step counter -- once per outermost forward entry point (a wrapping model's forward
+        marks its nested encoder / fusion calls with `_nested`)."""
+        if not getattr(self, "_nested", False):
+            self.step_counter += 1
 
     def cw(self, name: str) -> torch.Tensor:
         """GEMM weight in the compute dtype."""
@@ -537,9 +552,10 @@ class Engine:
             saved.update(flag=flag, probe_coef=beta * 2.0 ** (-epoch))
         return out, (saved if save else None)
 
-    def heads_bwd(self, saved, dloss: torch.Tensor):
-        """dloss: device fp32 [1] = d(objective)/d(loss). Returns grads w.r.t. hidden_states
-        (dict index -> [T,H] fp32 tensor) and accumulates head parameter grads."""
+    def heads_bwd(self, saved, dloss: torch.Tensor, dprob: Optional[torch.Tensor] = None):
+        """dloss: device fp32 [1] = d(objective)/d(loss); dprob: device fp32 [1] = d(objective)/d(prob_loss) when
+        someone differentiates the returned probe loss directly (None on the training path).  Returns grads w.r.t.
+        hidden_states (dict index -> [T,H] fp32 tensor) and accumulates head parameter grads."""
         c, f = self.cfg, self.flat
         B, Lq, H = saved["B"], saved["L"], c.H
         T = B * Lq
@@ -576,11 +592,17 @@ class Engine:
         if saved["use_probe"]:
             # loss += [prob_loss > 0.1] * prob_loss * beta * 2^-epoch  (probes/loss.py:14-16)
             dn = saved["dnorms"]
-            ops.scale_by_device_scalar(dn, dloss)
             flagf = saved["flag"].to(F32)          # 0/1 on device (tiny cast, plumbing)
-            ops.scale_by_device_scalar(dn, flagf)
+            if dprob is None:
+                ops.scale_by_device_scalar(dn, dloss)
+                ops.scale_by_device_scalar(dn, flagf)
+                alpha = 2.0 * saved["probe_coef"]
+            else:
+                # d/d(norms) of  dloss * [prob>0.1] * coef * prob  +  dprob * prob   (scalar glue on the device)
+                ops.scale_by_device_scalar(dn, (dloss * flagf * saved["probe_coef"] + dprob).contiguous())
+                alpha = 2.0
             Tm, x7 = saved["Tm"], saved["x7"]
-            dT = ops.rowscale(Tm, dn, 2.0 * saved["probe_coef"])
+            dT = ops.rowscale(Tm, dn, alpha)
             ops.linear_wgrad(x7, dT, f.g("oneWordpsdProbe.oneWordpsdProbe.proj"))
             projc = self.cw("oneWordpsdProbe.oneWordpsdProbe.proj")
             dx7 = ops.gemm(dT, projc, M=T, N=H, K=Tm.shape[1], out_dtype=self.compute_dtype)

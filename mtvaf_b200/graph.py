@@ -14,9 +14,14 @@ What makes the step replayable (nothing that changes per step may be a kernel AR
     NEXT batch host->device on a copy stream while the current replay runs.
 The reference has no counterpart (eager PyTorch, modules/train.py:859-885 `_step` + `optimizer.step()`); the
 reference-facing nn.Module API keeps working eagerly next to this.
+
+Construction does NOT train: the eager warm-up steps that prime the allocator pools / NCCL before the capture run on
+`example_batch`, and weights, Adam moments, gradient buffer, the optimizer clock (host `t` and device `dyn`) and the
+dropout step counter are snapshotted before and restored after it.  Step 1 of training is the first `__call__`.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -37,7 +42,12 @@ class GraphedTrainStep:
         self.consumed_event: Optional[torch.cuda.Event] = None
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         ops.set_step_source(self.step_dev)
+        # the registration is a process-global raw pointer: make sure it never outlives the tensor it points at
+        self._finalizer = weakref.finalize(self, ops.clear_step_source_if, self.step_dev.data_ptr())
         optimizer.enable_device_clock()
+        eng = optimizer.engine
+        eng.prepare()
+        snap = self._snapshot(eng, optimizer)
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
@@ -52,6 +62,31 @@ class GraphedTrainStep:
             self.loss = self._step()
         self.kernels_per_replay = ops.launch_count() - n0     # library kernels captured (NCCL / copies not counted)
         self.replays = 0
+        # dropout seeds are baked into the captured launches from the host counter as of the capture (the device
+        # counter `step_dev` is what varies per replay); tests replay the same masks eagerly from this value
+        self.captured_host_step = eng.step_counter
+        self._restore(eng, optimizer, snap)
+
+    @staticmethod
+    def _snapshot(eng, opt):
+        f = eng.flat
+        return dict(W=f.W.clone(), G=f.G.clone(), m=opt.m.clone(), v=opt.v.clone(), dyn=opt.dyn.clone(), t=opt.t,
+                    host_step=eng.step_counter)
+
+    def _restore(self, eng, opt, snap):
+        f = eng.flat
+        torch.cuda.synchronize(self.device)
+        f.W.copy_(snap["W"])
+        f.G.copy_(snap["G"])
+        opt.m.copy_(snap["m"])
+        opt.v.copy_(snap["v"])
+        opt.dyn.copy_(snap["dyn"])
+        opt.t = snap["t"]
+        eng.step_counter = snap["host_step"]
+        self.step_dev.zero_()
+        if eng.bf16:
+            f.refresh_bf16(force=True)
+        torch.cuda.synchronize(self.device)
 
     def _step(self) -> torch.Tensor:
         ops.advance_step(self.step_dev)
@@ -97,7 +132,7 @@ class GraphedTrainStep:
 
     def close(self):
         """Release the captured graph (and the NCCL kernels it references) and unregister the step counter."""
-        ops.set_step_source(None)
+        self._finalizer()
         if self.graph is not None:
             torch.cuda.synchronize(self.device)
             self.graph.reset()

@@ -227,6 +227,7 @@ class _HeadsFn(torch.autograd.Function):
         probe_layer = min(7, engine.cfg.n_layers)
         hs[probe_layer] = hs_probe.reshape(B * Lq, H) if hs_probe is not None else None
         need_grad = any(ctx.needs_input_grad) and labels is not None
+        ctx.set_materialize_grads(False)             # d(prob_loss) arrives as None unless someone backprops through it
         use_probe = bool(getattr(a, "use_probe", False))
         counted = None
         if img_losses is not None:
@@ -244,17 +245,20 @@ class _HeadsFn(torch.autograd.Function):
         model._last_heads = out
         loss = out["loss"] if out["loss"] is not None else torch.zeros(1, dtype=F32, device=mask.device)
         prob = out["prob_loss"] if out["prob_loss"] is not None else torch.zeros(1, dtype=F32, device=mask.device)
-        ctx.mark_non_differentiable(prob)
+        # prob_loss stays attached to autograd like the reference's: its gradient joins the probe
+        # branch of the heads backward
         return loss.view(()), prob.view(())
 
     @staticmethod
-    def backward(ctx, dloss, _dprob):
+    def backward(ctx, dloss, dprob):
         eng = ctx.engine
         if ctx.saved is None:
             raise L.MtvafError("backward through the heads needs labels (no loss was computed)")
         eng.flat.attach_grads()
-        dl = dloss.reshape(1).to(F32).contiguous()
-        grads = eng.heads_bwd(ctx.saved, dl)
+        dev = ctx.saved["seq_d"].device
+        dl = dloss.reshape(1).to(F32).contiguous() if dloss is not None else torch.zeros(1, dtype=F32, device=dev)
+        dp = None if dprob is None else dprob.reshape(1).to(F32).contiguous()
+        grads = eng.heads_bwd(ctx.saved, dl, dp)
         n = eng.cfg.n_layers
         d_last = grads[n].view(ctx.shape)
         d_probe = None
@@ -361,6 +365,7 @@ class _EncoderModelBase(nn.Module):
         eng = self.engine()
         eng.compute_dtype = self._compute_dtype if self._engine_owner is None else eng.compute_dtype
         eng.prepare()
+        eng.new_step()                       # fresh dropout masks per call (no-op inside a wrapping model's forward)
         B, Lq = input_ids.shape
         kv = self._pack_prefix(past_key_values, B, eng)
         P = 0 if kv is None else kv.shape[3] // self.config.hidden_size
@@ -401,38 +406,87 @@ class _EncoderModelBase(nn.Module):
                                   mode=L.EPI_TANH)
 
     def get_embedding_output(self, input_ids, token_type_ids=None, position_ids=None):
-        """models/modeling_roberta.py:980-988 (used by Cutoff, modules/augument.py:61)."""
+        """models/modeling_roberta.py:980-988 (used by Cutoff, modules/augument.py:61).  Differentiable like the
+        reference's: the embedding tables and the embedding LayerNorm receive gradients through it."""
+        if position_ids is not None:
+            raise L.MtvafError("explicit position_ids are not on the MTVAF path")
         eng = self.engine()
         eng.prepare()
+        eng.new_step()
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
-        c, f, e = eng.cfg, eng.flat, eng.enc_prefix
         B, Lq = input_ids.shape
-        with torch.no_grad():
-            x, _, _, _ = ops.embed_ln_fwd(input_ids, token_type_ids, f.w(e + "embeddings.word_embeddings.weight"),
-                                          f.w(e + "embeddings.position_embeddings.weight"),
-                                          f.w(e + "embeddings.token_type_embeddings.weight"),
-                                          f.w(e + "embeddings.LayerNorm.weight"), f.w(e + "embeddings.LayerNorm.bias"),
-                                          c.eps, 0 if c.kind == "roberta" else 1, c.pad_id, eng.compute_dtype,
-                                          c.hidden_dropout if self.training else 0.0, eng.seed(1))
+        x = _EmbedFn.apply(eng, input_ids.contiguous(), token_type_ids.contiguous(), self.training, self._anchor())
         return x.view(B, Lq, -1)
 
     def get_bert_output(self, embedding_output, attention_mask=None, past_key_values=None):
-        """models/modeling_roberta.py:990-1020: returns (sequence_output, pooled_output, attentions)."""
+        """models/modeling_roberta.py:990-1020: returns (sequence_output, pooled_output, attentions).  Gradients flow
+        back into `embedding_output` (Cutoff trains through it, modules/augument.py:75)."""
         eng = self.engine()
         eng.prepare()
+        eng.new_step()
         B, Lq, H = embedding_output.shape
         kv = self._pack_prefix(past_key_values, B, eng)
         P = 0 if kv is None else kv.shape[3] // H
-        text_mask = attention_mask[:, P:] if attention_mask.shape[1] == P + Lq else attention_mask
+        if attention_mask is None:
+            text_mask = torch.ones((B, Lq), dtype=torch.long, device=embedding_output.device)
+        elif attention_mask.shape[1] == P + Lq:
+            # the kernels attend to every prefix row (models/bert_model.py:490-492 builds those columns as ones);
+            # a caller that zeroes prefix columns must hear about it instead of getting silently different math
+            if P and not bool((attention_mask[:, :P] != 0).all()):
+                raise L.MtvafError("get_bert_output: masked-out prefix columns are not supported by the fused "
+                                   "prefix attention (all %d prefix columns must be 1)" % P)
+            text_mask = attention_mask[:, P:]
+        elif attention_mask.shape[1] == Lq:
+            text_mask = attention_mask
+        else:
+            raise L.MtvafError("attention_mask has %d columns, expected %d (prefix + text)"
+                               % (attention_mask.shape[1], P + Lq))
         ids = torch.zeros((B, Lq), dtype=torch.long, device=embedding_output.device)
         emb = embedding_output.reshape(B * Lq, H)
         if emb.dtype != eng.compute_dtype:
-            emb = emb.to(eng.compute_dtype)
+            emb = emb.to(eng.compute_dtype)          # differentiable cast (plumbing)
         outs = _EncoderFn.apply(eng, ids, ids, text_mask.to(torch.long).contiguous(), self.training, False,
                                 emb.contiguous(), self._anchor(), kv)
         last = outs[self.config.num_hidden_layers]
         return (last, _LazyPooler(self, last), None)
+
+
+class _EmbedFn(torch.autograd.Function):
+    """Embedding gather + LayerNorm (+dropout) as its own autograd node (get_embedding_output)."""
+
+    @staticmethod
+    def forward(ctx, engine: Engine, ids, tts, training, anchor):
+        c, f, e = engine.cfg, engine.flat, engine.enc_prefix
+        p_h = c.hidden_dropout if training else 0.0
+        seed = engine.seed(1)
+        x, pids, mean, rstd = ops.embed_ln_fwd(ids, tts, f.w(e + "embeddings.word_embeddings.weight"),
+                                               f.w(e + "embeddings.position_embeddings.weight"),
+                                               f.w(e + "embeddings.token_type_embeddings.weight"),
+                                               f.w(e + "embeddings.LayerNorm.weight"),
+                                               f.w(e + "embeddings.LayerNorm.bias"), c.eps,
+                                               0 if c.kind == "roberta" else 1, c.pad_id, engine.compute_dtype, p_h, seed)
+        ctx.engine, ctx.saved = engine, (ids, tts, pids, mean, rstd, p_h, seed)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        eng = ctx.engine
+        c, f, e = eng.cfg, eng.flat, eng.enc_prefix
+        ids, tts, pids, mean, rstd, p_h, seed = ctx.saved
+        f.attach_grads()
+        dx = dx.reshape(ids.numel(), c.H).contiguous()
+        if dx.dtype != eng.compute_dtype:
+            dx = ops.cast_bf16(dx) if eng.compute_dtype == BF16 else ops.cast_f32(dx)
+        ops.embed_ln_bwd(dx, ids, tts, pids, f.w(e + "embeddings.word_embeddings.weight"),
+                         f.w(e + "embeddings.position_embeddings.weight"),
+                         f.w(e + "embeddings.token_type_embeddings.weight"),
+                         f.w(e + "embeddings.LayerNorm.weight"), mean, rstd, 0 if c.kind == "roberta" else 1, c.pad_id,
+                         f.g(e + "embeddings.word_embeddings.weight"), f.g(e + "embeddings.position_embeddings.weight"),
+                         f.g(e + "embeddings.token_type_embeddings.weight"), f.g(e + "embeddings.LayerNorm.weight"),
+                         f.g(e + "embeddings.LayerNorm.bias"), p_h, seed)
+        ctx.saved = None
+        return (None,) * 5
 
 
 class _LazyPooler:
@@ -448,6 +502,17 @@ class _LazyPooler:
 
     def __getattr__(self, k):
         return getattr(self.tensor(), k)
+
+    def __getitem__(self, i):
+        return self.tensor()[i]
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        """torch.* functions see the materialised tensor (the reference returns a plain Tensor here)."""
+        un = lambda a: a.tensor() if isinstance(a, _LazyPooler) else a
+        args = tuple(un(a) for a in args)
+        kwargs = {k: un(v) for k, v in (kwargs or {}).items()}
+        return func(*args, **kwargs)
 
 
 class RobertaModel(_EncoderModelBase):
@@ -616,8 +681,15 @@ class ImageModel(nn.Module):
         name = "resnet152" if use_152 else "resnet101" if use_101 else "resnet34" if use_34 else \
             "resnet18" if use_18 else "resnet50"
         self.resnet = getattr(tvm, name)(weights=None)
-        if resnet_root is not None and os.path.exists(os.path.join(resnet_root, name + ".pth")):
-            self.resnet.load_state_dict(torch.load(os.path.join(resnet_root, name + ".pth")))
+        # the reference loads resnet_root/<name>.pth unconditionally (models/bert_model.py:84-85).  A mistyped path
+        # must not leave a randomly initialised frozen front-end behind: raise unless the caller opts out explicitly
+        # (resnet_root=None: offline / random-init runs, e.g. the synthetic benchmarks)
+        if resnet_root is not None:
+            path = os.path.join(resnet_root, name + ".pth")
+            if not os.path.exists(path):
+                raise FileNotFoundError("ImageModel: %s not found (pass resnet_root=None for a random-init "
+                                        "front-end)" % path)
+            self.resnet.load_state_dict(torch.load(path))
 
     def forward(self, x, aux_imgs=None):
         main = self.get_resnet_prompt(x)
@@ -688,9 +760,24 @@ class TVNetSAModel2(nn.Module):
         self.dropout = nn.Dropout(0.1)
         if args.use_probe:
             self.oneWordpsdProbe = probe(args={"probe": {"maximum_rank": H // 2}, "model": {"hidden_dim": H}})
-            ckpt = os.path.join(os.path.abspath("."), "models", "psdProbe_base_savel7.pt")
-            if os.path.exists(ckpt):       # models/bert_model.py:474-475
-                self.oneWordpsdProbe.load_state_dict(torch.load(ckpt, map_location="cpu", weights_only=False).state_dict())
+            # models/bert_model.py:474-475 loads ./models/psdProbe_base_savel7.pt unconditionally.  `args.probe_ckpt`
+            # overrides the path; "" / "none" = explicit opt-out (random-init probe: synthetic benchmarks, tests);
+            # a path that is given (or the reference's default when it exists) must load, a missing one warns loudly
+            ckpt = getattr(args, "probe_ckpt", None)
+            explicit = ckpt is not None
+            if ckpt is None:
+                ckpt = os.path.join(os.path.abspath("."), "models", "psdProbe_base_savel7.pt")
+            if str(ckpt).lower() not in ("", "none"):
+                if os.path.exists(ckpt):
+                    self.oneWordpsdProbe.load_state_dict(
+                        torch.load(ckpt, map_location="cpu", weights_only=False).state_dict())
+                elif explicit:
+                    raise FileNotFoundError("TVNetSAModel2: probe checkpoint %s not found" % ckpt)
+                else:
+                    import warnings
+                    warnings.warn("TVNetSAModel2: %s not found -- the psdProbe matrix stays randomly initialised "
+                                  "(the reference loads it unconditionally, models/bert_model.py:474-475); set "
+                                  "args.probe_ckpt to the file, or to '' to silence this" % ckpt)
             self.combineLoss = CombineLoss(args.beta)
         self._engine: Optional[Engine] = None
         self._compute_dtype = _resolve_dtype(getattr(args, "compute_dtype", None))
@@ -742,7 +829,7 @@ class TVNetSAModel2(nn.Module):
         if not input_ids.is_cuda:
             raise L.MtvafError("mtvaf_b200 runs on CUDA devices only (no CPU fallback); got %s" % input_ids.device)
         eng = self.engine()
-        eng.step_counter += 1
+        eng.new_step()
         eng.prepare()
         eng._nested = True
         try:
@@ -954,7 +1041,7 @@ class TVNetSAModel(nn.Module):
         if augument:
             raise L.MtvafError("Cutoff augmentation is outside the hot path (SURVEY.md 2, row 12)")
         eng = self.engine()
-        eng.step_counter += 1
+        eng.new_step()
         eng.prepare()
         eng._nested = True
         try:

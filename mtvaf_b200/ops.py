@@ -34,7 +34,7 @@ def _stream():
 
 # the library counts its own kernel launches (mtvaf_launch_count); the bench reports the count of OUR launches
 _launch_base = 0
-GEMM_EVENT_SINK = None      # bench.py: list receiving (start_event, end_event, flops, algorithmic bytes) per tcgen05 GEMM launch
+GEMM_EVENT_SINK = None      # bench.py: list receiving (start_event, end_event, flops, algorithmic bytes, (M, N, K, a_mn, b_mn, mode)) per tcgen05 GEMM launch
 
 
 def reset_launch_count():
@@ -105,7 +105,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         e1.record()
         nbytes = 2 * (M * K + N * K) + (M * N * out.element_size() if out is not None else 0)
         nbytes += (M * N * 2 if aux is not None else 0) + (M * N * 2 if out2 is not None else 0)
-        sink.append((e0, e1, 2.0 * M * N * K, nbytes))
+        sink.append((e0, e1, 2.0 * M * N * K, nbytes, (M, N, K, int(a_mn), int(b_mn), int(mode))))
     _check(rc, "mtvaf_gemm")
     return out
 
@@ -512,11 +512,24 @@ def adam_dyn_advance(dyn, b1, b2, warmup_steps, total_steps):
            "adam_dyn_advance")
 
 
+_STEP_SOURCE_PTR = 0
+
+
 def set_step_source(t: Optional[torch.Tensor]):
-    """Register (or clear) the device step counter every dropout site mixes into its seed (CUDA-graph replay)."""
+    """Register (or clear) the device step counter every dropout site mixes into its seed (CUDA-graph replay).
+    The registration is process-global (one training step per process)."""
+    global _STEP_SOURCE_PTR
     if t is not None:
         assert t.is_cuda and t.dtype == torch.int64 and t.numel() == 1
     _check(_raw.mtvaf_set_step_source(_p(t)), "set_step_source")
+    _STEP_SOURCE_PTR = 0 if t is None else t.data_ptr()
+
+
+def clear_step_source_if(ptr: int):
+    """Unregister the step counter iff `ptr` is still the registered one (finalizer of GraphedTrainStep: a dropped
+    step object must not leave a dangling device pointer behind, nor clear a newer object's registration)."""
+    if ptr and ptr == _STEP_SOURCE_PTR:
+        set_step_source(None)
 
 
 def advance_step(t: torch.Tensor):

@@ -67,6 +67,88 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_steps(rank, world, port, q):
+    """K optimizer steps through the path bench.py times at N > 1: per-layer all-reduce hooks inside backward,
+    `FlatAdamW.step(zero_grad=True, sync=...)` (tail all-reduce under the layer updates), eagerly and replayed from the
+    whole-step CUDA graph -- against one rank stepping on the full batches."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from mtvaf_b200 import synthetic as S
+        from mtvaf_b200.optim import GradSync, FlatAdamW
+        from mtvaf_b200.graph import GraphedTrainStep
+        K = 3
+        fulls = [S.make_batch(4, 32, vocab=1000, seed=90 + i) for i in range(K)]
+        halves = [{k: v[2 * rank:2 * rank + 2].to(dev) for k, v in b.items()} for b in fulls]
+
+        def loss_of(out):
+            return (out[0] if isinstance(out, tuple) else out).loss
+
+        m = _build(dev)
+        opt = FlatAdamW(m.engine(), lr=5e-5, warmup_steps=2, total_steps=10)
+        for b in fulls:
+            loss_of(m(**{k: v.to(dev) for k, v in b.items()})).backward()
+            opt.step(zero_grad=True)
+        W_full = m.engine().flat.W.clone()
+        res = {}
+        for mode in ("eager", "graph"):
+            m2 = _build(dev)
+            opt2 = FlatAdamW(m2.engine(), lr=5e-5, warmup_steps=2, total_steps=10)
+            sync = GradSync(m2.engine(), optimizer=opt2)
+            if mode == "eager":
+                for b in halves:
+                    loss_of(m2(**b)).backward()
+                    opt2.step(zero_grad=True, sync=sync)
+            else:
+                g = GraphedTrainStep(m2, opt2, halves[0], grad_sync=sync, warmup=2)
+                for b in halves:
+                    g(b)
+                torch.cuda.synchronize()
+                g.close()
+            torch.cuda.synchronize()
+            W = m2.engine().flat.W
+            f = m2.engine().flat
+            worst = 0.0
+            for n in f.names:
+                o, k = f.offsets[n]
+                nb = float(W_full[o:o + k].norm())
+                if nb > 0:
+                    worst = max(worst, float((W[o:o + k] - W_full[o:o + k]).norm()) / nb)
+            chk = torch.stack([W.double().sum(), W.double().abs().sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            res[mode] = (worst, bool(torch.equal(lo, hi)))
+        q.put((rank, res))
+    except Exception as e:                               # pragma: no cover
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_optimizer_steps_match_single_rank_and_ranks_stay_equal():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_steps, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for rank, r in res:
+        assert isinstance(r, dict), (rank, r)
+        for mode, (worst, equal) in r.items():
+            assert equal, (rank, mode, "ranks diverged")
+            assert worst < 1e-4, (rank, mode, worst)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_rank_gradients_match_single_rank_full_batch():
     ctx = mp.get_context("spawn")

@@ -110,10 +110,6 @@ def test_tvnet2_bert_backbone_fp32_matches_reference_golden(golden_dir):
     check_fp(fp, g["grad_fp"], 2e-3)
 
 
-@pytest.mark.skipif(os.environ.get("MTVAF_EXPERIMENTAL") != "1",
-                    reason="golden added at the end of round 1 with no GPU time left to run this test once: opt-in "
-                           "(MTVAF_EXPERIMENTAL=1) until it has passed on hardware; the oracle side is checked on CPU "
-                           "and test_tvnet2_no_prefix_no_probe_fp32 covers the product against the oracle")
 @pytest.mark.parametrize("variant", ["noauxloss", "no_vao", "no_probe", "no_prefix"])
 def test_tvnet2_flag_variants_fp32_match_reference_golden(golden_dir, variant):
     gold = _gold(golden_dir, "tvnet2_variants")

@@ -1,0 +1,275 @@
+"""Parity of WHAT bench.py TIMES: `GraphedTrainStep` (whole-step CUDA graph) -> `FlatAdamW.step(zero_grad=True)` with the
+device clock (`mtvaf_adam_dyn_advance`), the device step counter for dropout seeds (`mtvaf_set_step_source` /
+`mtvaf_advance_step`), against
+  (a) the same K steps issued eagerly (model -> backward -> FlatAdamW.step with the host clock), dropout ON with the same
+      step counter, and
+  (b) the oracle under autograd + torch.optim.AdamW + get_linear_schedule_with_warmup with the reference's parameter
+      groups (modules/train.py:894-921): loss trajectory and final weights, fp32 <= 1e-4, bf16 <= 2e-2.
+Tolerances on weights are norm-wise per tensor: the wgrad kernels accumulate split-K partial sums with fp32 atomics (order
+not fixed), and Adam's m/sqrt(v) turns a sign flip of a noise-level gradient element into a +-lr step, so element-wise
+bit equality is not a property of this path (of the reference's cuBLAS split-K path neither)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mtvaf_oracle as O
+from oracle.make_golden import hf_config
+from mtvaf_b200 import synthetic as S
+
+DEV = "cuda"
+LR = 5e-5
+K = 5
+
+
+def _build(cfg, params, dtype, train):
+    from mtvaf_b200.modules import TVNetSAModel2, FeatureStub
+    args = SimpleNamespace(bert_name="roberta-base", prefix_dim=768, prefix_len=4, use_prefix=True, use_probe=True,
+                           beta=0.5, alpha=0.1, vao=True, noauxloss=False, resnet_root=None, compute_dtype=dtype,
+                           n_gpu=1, probe_ckpt="")
+    m = TVNetSAModel2(list(range(10)), None, args, config=hf_config(cfg), image_model=FeatureStub())
+    m.load_state_dict(params, strict=False)
+    m = m.to(DEV)
+    m.train(train)
+    return m
+
+
+def _dev(b):
+    return {k: v.to(DEV) for k, v in b.items()}
+
+
+def _tensor_errors(f, W_a, W_b, W_0):
+    """Per parameter: ||a-b|| / ||b|| and ||a-b|| / ||b - w0|| (error relative to the distance travelled)."""
+    worst_w, worst_u, who = 0.0, 0.0, None
+    for n in f.names:
+        o, k = f.offsets[n]
+        a, b, w0 = W_a[o:o + k].double(), W_b[o:o + k].double(), W_0[o:o + k].double()
+        d = float((a - b).norm())
+        nb, nu = float(b.norm()), float((b - w0).norm())
+        if nb > 0 and d / nb > worst_w:
+            worst_w, who = d / nb, n
+        if nu > 1e-12:
+            worst_u = max(worst_u, d / nu)
+    return worst_w, worst_u, who
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_graph_replays_equal_eager_steps_with_dropout(dtype):
+    """K replays of the captured step == K eager steps: same dropout masks (device step counter), same AdamW clock
+    (device `dyn` vs host `t`), same zero-grad semantics.  Also: constructing the graph does not train."""
+    from mtvaf_b200 import ops
+    from mtvaf_b200.graph import GraphedTrainStep
+    from mtvaf_b200.optim import FlatAdamW
+    cfg = O.EncoderCfg.roberta_base(vocab_size=1000)
+    params = S.init_params(cfg, seed=41, ln_jitter=0.05)
+    batches = [_dev(S.make_batch(4, 32, vocab=1000, seed=50 + i)) for i in range(K)]
+
+    # ---- graph arm
+    mg = _build(cfg, params, dtype, train=True)
+    eg = mg.engine()
+    eg.base_seed = 777
+    og = FlatAdamW(eg, lr=LR, warmup_steps=2, total_steps=10)
+    W0 = eg.flat.W.clone()
+    g = GraphedTrainStep(mg, og, batches[0], warmup=2)
+    torch.cuda.synchronize()
+    assert torch.equal(eg.flat.W, W0), "constructing GraphedTrainStep changed the weights"
+    assert og.t == 0 and int(og.dyn[0]) == 0 and float(og.m.abs().max()) == 0.0 and float(og.v.abs().max()) == 0.0
+    assert float(eg.flat.G.abs().max()) == 0.0
+    g_losses = [float(g(b)) for b in batches]
+    torch.cuda.synchronize()
+    assert int(og.dyn[0]) == K and int(g.step_dev) == K
+    W_g, m_g = eg.flat.W.clone(), og.m.clone()
+    host_step = g.captured_host_step
+    g.close()
+    assert ops._STEP_SOURCE_PTR == 0
+
+    # ---- eager arm: host clock; the same (host step, device step) pair per step as the captured launches saw
+    me = _build(cfg, params, dtype, train=True)
+    ee = me.engine()
+    ee.base_seed = 777
+    oe = FlatAdamW(ee, lr=LR, warmup_steps=2, total_steps=10)
+    step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.set_step_source(step_dev)
+    try:
+        e_losses = []
+        for b in batches:
+            ops.advance_step(step_dev)
+            ee.step_counter = host_step - 1            # forward() increments it to the captured value
+            out, _, _ = me(**b)
+            out.loss.backward()
+            oe.step(zero_grad=True)
+            e_losses.append(float(out.loss))
+    finally:
+        ops.set_step_source(None)
+    torch.cuda.synchronize()
+    assert oe.t == K
+    ltol = 1e-5 if dtype == "fp32" else 2e-3
+    for a, b in zip(g_losses, e_losses):
+        assert abs(a - b) <= ltol * abs(b), (g_losses, e_losses)
+    worst_w, worst_u, who = _tensor_errors(ee.flat, W_g, ee.flat.W, W0)
+    print("graph vs eager (%s): losses %s | worst ||dW||/||W|| %.2e (%s), worst vs update %.2e"
+          % (dtype, g_losses, worst_w, who, worst_u))
+    assert worst_w < (1e-5 if dtype == "fp32" else 2e-4), (who, worst_w)
+    assert worst_u < (2e-2 if dtype == "fp32" else 0.2), worst_u
+    assert float((m_g - oe.m).norm() / oe.m.norm()) < (1e-4 if dtype == "fp32" else 2e-2)
+    # a dropped GraphedTrainStep must not leave its step counter registered (dangling raw pointer)
+    g2 = GraphedTrainStep(mg, og, batches[0], warmup=1)
+    assert ops._STEP_SOURCE_PTR == g2.step_dev.data_ptr()
+    del g2
+    import gc
+    gc.collect()
+    assert ops._STEP_SOURCE_PTR == 0
+
+
+def _oracle_trajectory(cfg, params, batches, warmup_steps, total_steps):
+    """The reference's optimizer setup (modules/train.py:894-921) over the oracle's parameters."""
+    from transformers.optimization import get_linear_schedule_with_warmup
+    p = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    groups = [dict(lr=LR, weight_decay=1e-2, params=[v for k, v in p.items() if "bert" in k and "pooler" not in k]),
+              dict(lr=LR, weight_decay=1e-2, params=[v for k, v in p.items() if "encoder_conv" in k or "gates" in k]),
+              dict(lr=5e-2, weight_decay=1e-2, params=[v for k, v in p.items() if "crf" in k or k.startswith("fc")])]
+    opt = torch.optim.AdamW(groups)
+    sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=warmup_steps, num_training_steps=total_steps)
+    losses = []
+    for b in batches:
+        o = O.tvnet2_forward(p, cfg, b, alpha=0.1, beta=0.5)
+        o["loss"].backward()
+        opt.step()
+        sched.step()
+        opt.zero_grad()
+        losses.append(float(o["loss"]))
+    return losses, p
+
+
+@pytest.mark.parametrize("dtype,graph", [("fp32", False), ("fp32", True), ("bf16", True)])
+def test_k_step_trajectory_matches_oracle_autograd_and_torch_adamw(dtype, graph):
+    """Dropout off (eval mode: RNG streams cannot match the CPU's).  (The pooler gets no gradient on this path, in the
+    reference neither -- SURVEY.md section 2a -- so AdamW never touches it: weight decay included.)"""
+    from mtvaf_b200.graph import GraphedTrainStep
+    from mtvaf_b200.optim import FlatAdamW
+    cfg = O.EncoderCfg.roberta_base(vocab_size=1000)
+    params = S.init_params(cfg, seed=43, ln_jitter=0.05)
+    cpu_batches = [S.make_batch(4, 32, vocab=1000, seed=60 + i) for i in range(K)]
+    ref_losses, p = _oracle_trajectory(cfg, params, cpu_batches, warmup_steps=2, total_steps=10)
+    m = _build(cfg, params, dtype, train=False)
+    eng = m.engine()
+    opt = FlatAdamW(eng, lr=LR, warmup_steps=2, total_steps=10)
+    losses = []
+    if graph:
+        g = GraphedTrainStep(m, opt, _dev(cpu_batches[0]), warmup=2)
+        for b in cpu_batches:
+            losses.append(float(g(_dev(b))))
+        g.close()
+    else:
+        for b in cpu_batches:
+            out, _, _ = m(**_dev(b))
+            out.loss.backward()
+            opt.step(zero_grad=True)
+            losses.append(float(out.loss))
+    torch.cuda.synchronize()
+    tol = 1e-4 if dtype == "fp32" else 2e-2
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= tol * abs(b), (losses, ref_losses)
+    worst, who, worst_head = 0.0, None, 0.0
+    moved = 0
+    for k, prm in m.named_parameters():
+        if k not in p:
+            continue
+        ref = p[k].detach()
+        err = float((prm.detach().cpu().double() - ref.double()).norm() / (ref.double().norm() + 1e-30))
+        if err > worst:
+            worst, who = err, k
+        if "crf" in k or k.startswith("fc"):
+            worst_head = max(worst_head, err)
+        if not torch.equal(ref, params[k]):
+            moved += 1
+    print("trajectory %s graph=%s: losses %s oracle %s | worst ||dW||/||W|| %.2e (%s), heads %.2e"
+          % (dtype, graph, losses, ref_losses, worst, who, worst_head))
+    assert moved > 150                          # bert.*, encoder_conv.*, crf.*, fc.* all stepped by the oracle optimizer
+    assert worst < tol, (who, worst)
+    # parameters the reference's optimizer never steps (projectors, ANP heads, probe) must not have moved
+    for k in ("projectors.0.weight", "img_classifier.weight", "oneWordpsdProbe.oneWordpsdProbe.proj"):
+        assert torch.equal(dict(m.named_parameters())[k].detach().cpu(), params[k]), k
+
+
+def test_device_lr_schedule_equals_get_linear_schedule_with_warmup():
+    """mtvaf_adam_dyn_advance's factor for steps 1..N == transformers' schedule (modules/train.py:118-120,919-921)."""
+    import struct
+    from transformers.optimization import get_linear_schedule_with_warmup
+    from mtvaf_b200 import ops
+    warm, total = 3, 17
+    w = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([w], lr=1.0)
+    sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=warm, num_training_steps=total)
+    dyn = torch.zeros(3, dtype=torch.int64, device=DEV)
+    for step in range(total + 2):
+        want = opt.param_groups[0]["lr"]                   # factor applied to the step about to be taken
+        ops.adam_dyn_advance(dyn, 0.9, 0.999, warm, total)
+        raw = dyn.cpu().numpy().tobytes()
+        t, lr_scale, bc1, bc2s = struct.unpack("<Qfff", raw[:20])
+        assert t == step + 1
+        assert abs(lr_scale - want) < 1e-6, (step, lr_scale, want)
+        assert abs(bc1 - (1 - 0.9 ** t)) < 1e-6 and abs(bc2s - (1 - 0.999 ** t) ** 0.5) < 1e-6
+        opt.step()
+        sched.step()
+
+
+def test_prob_loss_is_attached_to_autograd():
+    """the returned prob_loss is differentiable in the reference.  d(prob_loss)/d(proj) against the
+    oracle (fp32)."""
+    cfg = O.EncoderCfg.roberta_base(vocab_size=800)
+    params = S.init_params(cfg, seed=47, ln_jitter=0.05)
+    batch = S.make_batch(3, 24, vocab=800, seed=48)
+    p = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    o = O.tvnet2_forward(p, cfg, batch, alpha=0.1, beta=0.5)
+    o["prob_loss"].backward()
+    m = _build(cfg, params, "fp32", train=False)
+    out, prob, img = m(**_dev(batch))
+    assert prob.requires_grad
+    prob.backward()
+    for k in ("oneWordpsdProbe.oneWordpsdProbe.proj", "bert.encoder.layer.3.output.dense.weight",
+              "bert.embeddings.word_embeddings.weight"):
+        ref = p[k].grad
+        got = dict(m.named_parameters())[k].grad.cpu()
+        assert float((got - ref).norm() / ref.norm()) < 1e-3, k
+    assert float(dict(m.named_parameters())["fc.weight"].grad.abs().max()) == 0.0
+
+
+def test_embedding_output_entry_points_are_differentiable():
+    """get_embedding_output / get_bert_output (modules/augument.py:61,75 Cutoff): gradients reach the embedding tables
+    (ADVICE r1), and equal those of the one-shot forward."""
+    from mtvaf_b200.modules import RobertaModel
+    cfg = O.EncoderCfg.roberta_base(vocab_size=600)
+    params = S.init_params(cfg, seed=49, ln_jitter=0.05, with_fusion=False)
+    sd = {k[len("bert."):]: v for k, v in params.items() if k.startswith("bert.")}
+    batch = S.make_batch(3, 24, vocab=600, seed=50, with_images=False)
+    ids, mask = batch["input_ids"].to(DEV), batch["attention_mask"].to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    w = torch.randn(3, 24, 768, generator=gen).to(DEV)
+    grads = []
+    for two_stage in (False, True):
+        m = RobertaModel.from_config(hf_config(cfg), compute_dtype="fp32")
+        m.load_state_dict(sd, strict=False)
+        m = m.to(DEV).eval()
+        if two_stage:
+            emb = m.get_embedding_output(ids)
+            assert emb.requires_grad
+            last = m.get_bert_output(emb, attention_mask=mask)[0]
+        else:
+            last = m(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+        (last * w).sum().backward()
+        grads.append({k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None})
+    for k in ("embeddings.word_embeddings.weight", "embeddings.LayerNorm.weight",
+              "encoder.layer.0.attention.self.query.weight"):
+        a, b = grads[1][k], grads[0][k]
+        assert float((a - b).norm() / b.norm()) < 1e-5, k
+    # a zeroed prefix column must be refused, not silently ignored
+    from mtvaf_b200 import lib
+    m = RobertaModel.from_config(hf_config(cfg), compute_dtype="fp32").to(DEV).eval()
+    pkv = [(k.to(DEV), v.to(DEV)) for k, v in S.make_prefix(3, 12, 12, 4)]
+    bad = torch.cat([torch.ones(3, 4, device=DEV), mask.float()], 1)
+    bad[0, 1] = 0
+    with pytest.raises(lib.MtvafError):
+        m.get_bert_output(m.get_embedding_output(ids), attention_mask=bad, past_key_values=pkv)
