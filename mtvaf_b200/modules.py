@@ -188,8 +188,7 @@ class _EncoderFn(torch.autograd.Function):
         ctx.saved = None
         if dkv is not None and ctx.kv_dtype == BF16:
             dkv = ops.cast_bf16(dkv)
-        if demb is not None:
-            demb = demb.view(grads[n].shape) if grads[n] is not None else demb
+        # (`embeds` entered as [T, H]; its gradient leaves in the same shape)
         return (None, None, None, None, None, None, demb, None, dkv)
 
 

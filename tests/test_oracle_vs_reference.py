@@ -29,14 +29,15 @@ def test_tvnet2_live_reference_forward_backward():
     p = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
     o = O.tvnet2_forward(p, cfg, batch, alpha=0.1, beta=0.5)
     o["loss"].backward()
-    torch.testing.assert_close(o["loss"], out.loss.detach(), rtol=1e-5, atol=1e-5)
-    torch.testing.assert_close(o["prob_loss"], prob_loss.detach(), rtol=1e-5, atol=1e-3)
-    torch.testing.assert_close(o["img_loss"], img_loss.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(o["loss"], out.loss.detach().cpu(), rtol=1e-5, atol=1e-5)
+    # (the reference's probe moves norms / labels to "cuda:0" whenever a GPU exists, probes/probe_trainModel.py:16-17)
+    torch.testing.assert_close(o["prob_loss"], prob_loss.detach().cpu(), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(o["img_loss"], img_loss.detach().cpu(), rtol=1e-5, atol=1e-6)
     assert o["logits"] == out.logits
     ref_grads = dict(model.named_parameters())
     for k in ("fc.weight", "crf.transitions", "encoder_conv.0.weight", "bert.encoder.layer.0.attention.self.query.weight",
               "bert.encoder.layer.11.output.dense.weight", "bert.embeddings.word_embeddings.weight"):
-        g_ref, g = ref_grads[k].grad, p[k].grad
+        g_ref, g = ref_grads[k].grad.cpu(), p[k].grad
         assert g_ref is not None and g is not None, k
         n = float(g_ref.norm())
         assert float((g - g_ref).norm()) <= 5e-4 * n + 1e-7, k

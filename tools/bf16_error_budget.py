@@ -81,8 +81,9 @@ def main():
                 W, bvec = fit_head(e32[12].reshape(-1, 768), batch["labels"].reshape(-1),
                                    batch["attention_mask"].reshape(-1).bool())
                 for m in (m32, m16):
-                    m.fc.weight.data.copy_(W)
-                    m.fc.bias.data.copy_(bvec)
+                    with torch.no_grad():            # in-place on the Parameter: bumps its version -> bf16 shadow refreshed
+                        m.fc.weight.copy_(W)
+                        m.fc.bias.copy_(bvec)
             o32, p32, i32, em32, h32 = run(m32, batch)
             o16, p16, i16, em16, h16 = run(m16, batch)
             t32 = [t for s in o32.logits for t in s]
