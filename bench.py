@@ -427,6 +427,10 @@ def main():
     host = []
     for i in range(n_host):
         b = S.make_batch(B, L_TEXT, shape=w["shape"], seed=2024 + 100 * rank + i, with_images=w["prefix"])
+        if w["prefix"] and args.dtype == "bf16":
+            # visual features travel in the bf16 wire format of the offline front-end stage (mtvaf_b200/features.py):
+            # the fusion GEMM consumes bf16 anyway, so this is bit-identical to feeding fp32 features in bf16 mode
+            b["images"], b["aux_imgs"] = b["images"].to(torch.bfloat16), b["aux_imgs"].to(torch.bfloat16)
         host.append({k: v.pin_memory() for k, v in b.items()})
     resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())

@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-#define MTVAF_ABI_VERSION 2   /* 2: MtvafEpilogue.colsum, mtvaf_attention_bwd_ex, mtvaf_set_sm_reserve */
+#define MTVAF_ABI_VERSION 3   /* 2: MtvafEpilogue.colsum, mtvaf_attention_bwd_ex, mtvaf_set_sm_reserve
+                               * 3: mtvaf_set_pairwise_impl, mtvaf_pack_features (tcgen05 TwoWord probe; feature wire format) */
 #define MTVAF_F32 0
 #define MTVAF_BF16 1
 
@@ -223,13 +224,25 @@ int mtvaf_mean4_bwd_add(const float* dy, float* dx, int64_t rows, int W, int mod
 int mtvaf_softmax_kl_fwd_bwd(const float* logits, int64_t ld, const float* target, int rows, int B, int n,
                              float* loss_per_head, float* dlogits, float grad_scale, void* stream);
 
+/* ---- visual features: wire format -> GEMM operand (models/bert_model.py:536-539) ------------------ */
+/* images [B, E] (samples `img_ld` elements apart), aux_imgs [B, n_aux, E] (samples `aux_ld` apart; both `in_dtype`:
+ * fp32, or bf16 = the cached wire format of the frozen ResNet pyramid, E = 3840*2*2) -> out [1 + n_aux, B, E] in
+ * `out_dtype`: the cat + view + aux permute + cast of get_visual_prompt's first lines in one pass.  E and the strides
+ * % 8 == 0, 16-byte aligned pointers. */
+int mtvaf_pack_features(const void* images, int64_t img_ld, const void* aux_imgs, int64_t aux_ld, int in_dtype, int B,
+                        int n_aux, int64_t E, void* out, int out_dtype, void* stream);
+
 /* ---- psdProbe: probes/probe.py:74-78, probes/constructLabel.py:11-29, probes/probe_trainModel.py:23-24 */
 /* bit-exact pseudo labels (stable sort + sequential fp32 scan) for norms [B, L] fp32 -> labels [B, L] fp32 */
 int mtvaf_probe_labels(const float* norms, float* labels, int B, int L, void* stream);
 /* loss[0] = mean((norms-labels)^2) ; dnorms (optional) = 2 (norms-labels) / (B L) */
 int mtvaf_mse_fwd_bwd(const float* norms, const float* labels, int64_t n, float* loss, float* dnorms, void* stream);
-/* TwoWordPSDProbe probes/probe.py:25-46: dist[b,i,j] = sum_r (T[b,i,r]-T[b,j,r])^2, explicit differences */
+/* TwoWordPSDProbe probes/probe.py:25-46: dist[b,i,j] = sum_r (T[b,i,r]-T[b,j,r])^2.  fp32 T with R % 64 == 0: Gram form
+ * on the tcgen05 tensor cores (bf16 hi/lo split, fp32-class accuracy; diagonal exactly 0, exactly symmetric,
+ * near-duplicate pairs recomputed from explicit differences); otherwise the SIMT explicit-difference kernel. */
 int mtvaf_pairwise_sqdist(const void* T, int64_t ld, int dtype, int B, int L, int R, float* dist, void* stream);
+/* 0 = auto, 1 = always the SIMT explicit-difference kernel (A/B testing; process-global) */
+int mtvaf_set_pairwise_impl(int impl);
 
 /* ---- linear-chain CRF (pytorch-crf semantics; call sites bert_model.py:464,511,521) ----------- */
 /* emissions [B, L, T] fp32, tags [B, L] int64, mask [B, L] int64 (mask[:,0] must be 1).

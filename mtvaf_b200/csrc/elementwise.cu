@@ -494,6 +494,47 @@ extern "C" int mtvaf_adamw_step(float* param, float* grad, float* exp_avg, float
   return 0;
 }
 
+// ---- feature wire format: [B, E] + [B, n_aux, E] (fp32 / bf16) -> [1 + n_aux, B, E] (fp32 / bf16), 8 elements per thread
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+pack_features_kernel(const TI* __restrict__ img, long long img_ld, const TI* __restrict__ aux, long long aux_ld, int B,
+                     int n_aux, long long E8, TO* __restrict__ out) {
+  const long long per_img = (long long)B * E8;
+  const long long total = per_img * (1 + n_aux);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / per_img);
+    const long long rem = i - (long long)j * per_img;
+    const long long b = rem / E8, e = rem - b * E8;
+    const TI* src = j == 0 ? img + b * img_ld + e * 8 : aux + b * aux_ld + ((long long)(j - 1) * E8 + e) * 8;
+    float v[8];
+    Vec8<TI>::load(src, v);
+    Vec8<TO>::store(out + i * 8, v);
+  }
+}
+
+extern "C" int mtvaf_pack_features(const void* images, int64_t img_ld, const void* aux_imgs, int64_t aux_ld, int in_dtype,
+                                   int B, int n_aux, int64_t E, void* out, int out_dtype, void* stream) {
+  MTVAF_REQUIRE(images && out && B > 0 && n_aux >= 0 && E > 0 && E % 8 == 0, "pack_features: bad argument");
+  MTVAF_REQUIRE(img_ld % 8 == 0 && aux_ld % 8 == 0, "pack_features: sample strides must be multiples of 8 elements");
+  MTVAF_REQUIRE(n_aux == 0 || aux_imgs, "pack_features: aux_imgs missing");
+  MTVAF_REQUIRE(((reinterpret_cast<uintptr_t>(images) | reinterpret_cast<uintptr_t>(out) |
+                  reinterpret_cast<uintptr_t>(aux_imgs)) & 15) == 0, "pack_features: pointers must be 16-byte aligned");
+  const long long E8 = E / 8, total = (long long)B * E8 * (1 + n_aux);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MTVAF_PACK(TI, TO) \
+  pack_features_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)images, img_ld, (const TI*)aux_imgs, aux_ld, B, n_aux, \
+                                                     E8, (TO*)out)
+  if (in_dtype == MTVAF_F32 && out_dtype == MTVAF_F32) MTVAF_PACK(float, float);
+  else if (in_dtype == MTVAF_F32 && out_dtype == MTVAF_BF16) MTVAF_PACK(float, __nv_bfloat16);
+  else if (in_dtype == MTVAF_BF16 && out_dtype == MTVAF_F32) MTVAF_PACK(__nv_bfloat16, float);
+  else if (in_dtype == MTVAF_BF16 && out_dtype == MTVAF_BF16) MTVAF_PACK(__nv_bfloat16, __nv_bfloat16);
+  else MTVAF_REQUIRE(false, "pack_features: unsupported dtype");
+#undef MTVAF_PACK
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mtvaf_adam_dyn_advance(void* dyn, float beta1, float beta2, int warmup_steps, int total_steps,
                                       void* stream) {
   MTVAF_REQUIRE(dyn && reinterpret_cast<uintptr_t>(dyn) % 8 == 0, "adam_dyn_advance: bad pointer");

@@ -519,9 +519,23 @@ extern "C" int mtvaf_probe_labels(const float* norms, float* labels, int B, int 
   return 0;
 }
 
+namespace mtvaf {
+bool pairwise_tc_supported(const void* T, int64_t ld, int dtype, int R);            // pairwise_tc.cu
+int pairwise_tc_launch(const float* T, int64_t ld, int B, int L, int R, float* dist, cudaStream_t st);
+}  // namespace mtvaf
+static int g_pairwise_impl = 0;
+extern "C" int mtvaf_set_pairwise_impl(int impl) {
+  MTVAF_REQUIRE(impl == 0 || impl == 1, "pairwise impl must be 0 (auto: tcgen05 Gram form when supported) or 1 (SIMT explicit differences)");
+  g_pairwise_impl = impl;
+  return 0;
+}
+
 extern "C" int mtvaf_pairwise_sqdist(const void* T, int64_t ld, int dtype, int B, int L, int R, float* dist,
                                      void* stream) {
   MTVAF_REQUIRE(T && dist && B > 0 && L > 0 && R > 0, "pairwise_sqdist: bad argument");
+  // fp32 projected tokens with R % 64 == 0 (the probe ranks 384 / 512): Gram form on the tensor cores
+  if (g_pairwise_impl == 0 && pairwise_tc_supported(T, ld, dtype, R))
+    return pairwise_tc_launch((const float*)T, ld, B, L, R, dist, (cudaStream_t)stream);
   dim3 grid((L + 15) / 16, (L + 15) / 16, B);
   if (dtype == MTVAF_BF16)
     pairwise_sqdist_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)T, ld, L, R, dist);

@@ -402,7 +402,8 @@ class Engine:
     # ------------------------------------------------------------------ fusion (visual prompt)
     def fusion_fwd(self, feats: torch.Tensor, imagelabel: Optional[torch.Tensor], vao: bool, training: bool,
                    save: bool, n_aux_heads: int):
-        """feats [n_img, B, 4, 3840] fp32 pyramid rows (image 0 = full image, 1.. = aux crops).
+        """feats [n_img, B, 4, 3840] pyramid rows, fp32 or already in the compute dtype (image 0 = full image, 1.. = aux
+        crops).
         Returns (kv [n_layers,2,B,P*H] compute dtype, img_losses [n_img] fp32 or None, saved)."""
         c, f = self.cfg, self.flat
         cd = self.compute_dtype
@@ -411,10 +412,12 @@ class Engine:
         W8 = 8 * H
         rows4 = n_img * B * 4
         x = feats.reshape(rows4, feats.shape[-1])
-        if cd == BF16:
+        if x.dtype == cd:
+            x = x.contiguous()                      # packed by mtvaf_pack_features in the GEMM dtype already
+        elif cd == BF16:
             x = ops.cast_bf16(x.contiguous())
         else:
-            x = x.contiguous()
+            x = ops.cast_f32(x.contiguous())
         h1 = ops.linear_fwd(x, self.cw("encoder_conv.0.weight"), f.w("encoder_conv.0.bias"), mode=L.EPI_TANH)
         guids = ops.linear_fwd(h1, self.cw("encoder_conv.2.weight"), f.w("encoder_conv.2.bias"))     # [rows4, 8H]
         rows = n_img * B

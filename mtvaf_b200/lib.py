@@ -70,6 +70,8 @@ SIGNATURES = {
     "mtvaf_probe_labels": [_vp, _vp, _i, _i, _vp],
     "mtvaf_mse_fwd_bwd": [_vp, _vp, _i64, _vp, _vp, _vp],
     "mtvaf_pairwise_sqdist": [_vp, _i64, _i, _i, _i, _i, _vp, _vp],
+    "mtvaf_set_pairwise_impl": [_i],
+    "mtvaf_pack_features": [_vp, _i64, _vp, _i64, _i, _i, _i, _i64, _vp, _i, _vp],
     "mtvaf_crf_nll_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
     "mtvaf_crf_decode": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtvaf_span_offsets": [_vp, _i, _i, _vp, _vp],

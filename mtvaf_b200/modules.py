@@ -711,8 +711,11 @@ class ImageModel(nn.Module):
 
 class FeatureStub(nn.Module):
     """Takes packed pyramid features images [B,3840,2,2], aux_imgs [B,n_aux,3840,2,2] (the fusion
-    boundary of SURVEY.md 8(d)) and returns them in ImageModel's list-of-4 layout."""
+    boundary of SURVEY.md 8(d); fp32, or bf16 = the cached wire format of mtvaf_b200.features) and returns them in
+    ImageModel's list-of-4 layout.  The models recognise `packed_features` and hand the tensors to
+    `mtvaf_pack_features` directly instead of going through split / cat / stack."""
     WIDTHS = (256, 512, 1024, 2048)
+    packed_features = True
 
     def forward(self, x, aux_imgs=None):
         main = list(torch.split(x, self.WIDTHS, dim=1))
@@ -798,6 +801,18 @@ class TVNetSAModel2(nn.Module):
         """[n_img, B, 4, 3840] fp32 rows exactly as :538-539 build them (cat over the 4 pyramid levels,
         then a plain view(bsz, prefix_len, -1))."""
         with torch.no_grad():
+            if getattr(self.image_model, "packed_features", False) and images.is_cuda:
+                # features arrive packed (FeatureStub / the feature cache): one kernel does cat + view + aux permute +
+                # cast to the GEMM dtype (fp32 or bf16 wire format in)
+                if aux_imgs is not None and aux_imgs.dtype != images.dtype:
+                    aux_imgs = aux_imgs.to(images.dtype)
+                eng = self.engine()
+                if not images[0].is_contiguous():
+                    images = images.contiguous()
+                if aux_imgs is not None and not aux_imgs[0].is_contiguous():
+                    aux_imgs = aux_imgs.contiguous()
+                out = ops.pack_features(images, aux_imgs, eng.compute_dtype)
+                return out.view(out.shape[0], out.shape[1], self.args.prefix_len, -1)
             main, aux = self.image_model(images, aux_imgs)
             B = images.size(0)
             feats = [torch.cat(main, dim=1).reshape(B, self.args.prefix_len, -1)]

@@ -425,6 +425,30 @@ def pairwise_sqdist(T, B, Lq, R):
     return dist
 
 
+def set_pairwise_impl(impl: str):
+    """'auto' (tcgen05 Gram form for fp32 T with R % 64 == 0) or 'simt' (explicit differences) -- A/B testing."""
+    _check(_raw.mtvaf_set_pairwise_impl({"auto": 0, "simt": 1}[impl]), "set_pairwise_impl")
+
+
+def pack_features(images: torch.Tensor, aux_imgs: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+    """Feature wire format -> GEMM operand: images [B, E...] and aux_imgs [B, n_aux, E...] (fp32 or bf16, E = 3840*2*2
+    elements per image) -> [1 + n_aux, B, E] in `out_dtype`; row j*B + b = image j of sample b (models/bert_model.py:
+    536-539: cat of the pyramid levels + plain view, aux images permuted to the front)."""
+    _cuda(images, aux_imgs)
+    B = images.shape[0]
+    E = images.numel() // B
+    n_aux = 0 if aux_imgs is None else aux_imgs.shape[1]
+    # each sample's block must be dense; the stride BETWEEN samples is free (views of one [B, 1+n_aux, E] wire buffer)
+    assert images[0].is_contiguous()
+    assert aux_imgs is None or (aux_imgs[0].is_contiguous() and aux_imgs.dtype == images.dtype
+                                and aux_imgs.numel() == B * n_aux * E)
+    out = torch.empty((1 + n_aux, B, E), dtype=out_dtype, device=images.device)
+    _check(_raw.mtvaf_pack_features(images.data_ptr(), images.stride(0), _p(aux_imgs),
+                                    0 if aux_imgs is None else aux_imgs.stride(0), dt(images), B, n_aux, E,
+                                    out.data_ptr(), dt(out), _stream()), "pack_features")
+    return out
+
+
 def crf_nll(em, tags, mask, start, end, trans, want_grad, grad_scale):
     B, Lq, T = em.shape
     nll = torch.zeros(1, dtype=torch.float32, device=em.device)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         if n not in ("mtvaf_last_error", "mtvaf_launch_count"):
             assert n in lib.SIGNATURES, n
     hdr = open(os.path.join(ROOT, "include", "mtvaf_b200.h")).read()
-    assert lib.abi_version() == int(re.search(r"#define MTVAF_ABI_VERSION (\d+)", hdr).group(1)) == 2
+    assert lib.abi_version() == int(re.search(r"#define MTVAF_ABI_VERSION (\d+)", hdr).group(1)) == 3
     # the ctypes mirror of MtvafEpilogue must have the header's fields, in order
     body = re.search(r"typedef struct MtvafEpilogue \{(.*?)\} MtvafEpilogue;", hdr, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -76,4 +76,4 @@ def test_header_is_valid_c99_and_links_from_c(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     a, b = r.stdout.split()
-    assert a == b == "2"
+    assert a == b == "3"

@@ -175,6 +175,7 @@ def test_sweep_probes(layer, Lq):
     x = torch.randn(B, Lq, H, generator=g)
     ref1 = O.one_word_psd_probe(x, proj)
     ref2 = O.two_word_psd_probe(x[:, :64], proj)            # the explicit [B,L,L,r] difference tensor: keep it small
+    ref2_full = torch.stack([O.two_word_psd_probe(x[b:b + 1], proj)[0] for b in range(B)]) if Lq <= 128 else None
     xd, pd = x.to(DEV), proj.to(DEV)
     T = ops.linear_fwd(xd.view(B * Lq, H), pd.t().contiguous(), None)
     norms = (T * T).sum(-1).view(B, Lq)
@@ -183,6 +184,17 @@ def test_sweep_probes(layer, Lq):
     D = ops.pairwise_sqdist(T64, B, 64, T64.shape[1])
     assert rel(D, ref2) < 1e-4
     assert torch.equal(D, D.transpose(1, 2)) and float(D.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    # the full text length through the drop-in module (tcgen05 Gram form, several 128-token tiles at L=512)
+    from mtvaf_b200.modules import TwoWordPSDProbe
+    tw = TwoWordPSDProbe({"probe": {"maximum_rank": R}, "model": {"hidden_dim": H}}).to(DEV)
+    with torch.no_grad():
+        tw.proj.copy_(pd)
+    Dm = tw(xd)
+    assert Dm.shape == (B, Lq, Lq) and torch.equal(Dm, Dm.transpose(1, 2))
+    assert float(Dm.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    assert rel(Dm[:, :64, :64], ref2) < 1e-4
+    if ref2_full is not None:
+        assert rel(Dm, ref2_full) < 1e-4
     # pseudo labels from the depth norms: integer-valued, bit-exact against the restated rule
     lab = ops.probe_labels(norms)
     assert torch.equal(lab.cpu(), O.construct_label(norms.cpu()))

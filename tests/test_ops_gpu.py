@@ -645,6 +645,55 @@ def test_mse_and_pairwise(ops):
     assert torch.equal(dist, dist.transpose(1, 2))
 
 
+@pytest.mark.parametrize("B,Lq,R", [(3, 64, 384), (2, 128, 384), (2, 200, 512), (2, 512, 384), (1, 130, 64)])
+def test_pairwise_sqdist_tcgen05_gram_form(ops, B, Lq, R):
+    """TwoWordPSDProbe (probes/probe.py:25-46) on the tensor cores: Gram form with the bf16 hi/lo split against the
+    reference's explicit differences in float64 -- <= 1e-4 (max-norm), exactly symmetric, diagonal exactly 0,
+    duplicated and near-duplicated rows (cancellation) included; against the SIMT explicit-difference kernel too."""
+    T = rnd(B * Lq, R, seed=300 + Lq, scale=0.7)
+    T[7] = T[9]                                         # identical rows -> exactly 0
+    T[Lq - 1] = T[3] * (1 + 1e-4)                       # near-duplicates: d ~ 1e-8 |t|^2, below the Gram form's digits
+    T[11] = T[12] + 1e-3 * rnd(R, seed=5)
+    t = T.view(B, Lq, R).double().cpu()
+    ref = torch.stack([((t[b].unsqueeze(1) - t[b].unsqueeze(0)) ** 2).sum(-1) for b in range(B)])
+    dist = ops.pairwise_sqdist(T, B, Lq, R)
+    try:
+        ops.set_pairwise_impl("simt")
+        dist_simt = ops.pairwise_sqdist(T, B, Lq, R)
+    finally:
+        ops.set_pairwise_impl("auto")
+    assert rel_err(dist_simt, ref.float()) < 1e-5
+    err = rel_err(dist, ref.float())
+    print("pairwise Gram form B=%d L=%d R=%d: max-norm rel err %.2e" % (B, Lq, R, err))
+    assert err < 1e-4
+    assert torch.equal(dist, dist.transpose(1, 2))
+    assert float(dist.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    assert float(dist[0, 7, 9]) == 0.0 and float(dist.min()) >= 0.0
+    # the pairs the Gram form cannot resolve keep the reference's RELATIVE accuracy (explicit fix-up)
+    for (i, j) in ((Lq - 1, 3), (11, 12)):
+        r = float(ref[0, i, j])
+        assert abs(float(dist[0, i, j]) - r) <= 1e-3 * r, (i, j, float(dist[0, i, j]), r)
+    # element-wise relative accuracy away from the cancellation regime
+    big = ref > 1e-2 * ref.max()
+    assert float(((dist.cpu().double() - ref).abs() / ref.clamp_min(1e-30))[big].max()) < 1e-4
+
+
+def test_pack_features_wire_format(ops):
+    """mtvaf_pack_features == cat(pyramid) + view(B, 4, -1) + aux permute + cast (models/bert_model.py:536-539), from
+    fp32 features and from the bf16 wire format."""
+    B, n_aux = 5, 3
+    img = rnd(B, 3840, 2, 2, seed=11).abs()
+    aux = rnd(B, n_aux, 3840, 2, 2, seed=12).abs()
+    want = torch.stack([img.reshape(B, 4, -1)] + [aux[:, j].reshape(B, 4, -1) for j in range(n_aux)])   # [n_img,B,4,3840]
+    for in_dt in (torch.float32, torch.bfloat16):
+        for out_dt in (torch.float32, torch.bfloat16):
+            got = ops.pack_features(img.to(in_dt), aux.to(in_dt), out_dt)
+            assert got.shape == (1 + n_aux, B, 3840 * 4) and got.dtype == out_dt
+            assert torch.equal(got.view(1 + n_aux, B, 4, 3840), want.to(in_dt).to(out_dt))
+    got = ops.pack_features(img, None, torch.bfloat16)
+    assert torch.equal(got.view(1, B, 4, 3840), want[:1].to(torch.bfloat16))
+
+
 # ---------------------------------------------------------------------------------------- CRF
 def test_crf(ops):
     g = torch.Generator().manual_seed(4)
