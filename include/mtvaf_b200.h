@@ -24,7 +24,8 @@ extern "C" {
 #endif
 
 #define MTVAF_ABI_VERSION 3   /* 2: MtvafEpilogue.colsum, mtvaf_attention_bwd_ex, mtvaf_set_sm_reserve
-                               * 3: mtvaf_set_pairwise_impl, mtvaf_pack_features (tcgen05 TwoWord probe; feature wire format) */
+                               * 3: mtvaf_set_pairwise_impl, mtvaf_pack_features (tcgen05 TwoWord probe; feature wire format),
+                               *    mtvaf_attention_fwd_ws / _workspace_bytes (long-text tcgen05 attention) */
 #define MTVAF_F32 0
 #define MTVAF_BF16 1
 
@@ -170,10 +171,17 @@ int mtvaf_layernorm_bwd(const void* dy, const void* z, const float* gamma, const
 int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P,
                         const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx, float* lse,
                         float* probs, int dtype, float p_drop, uint64_t seed, void* stream);
-/* 0 (default) = tcgen05 kernels whenever dtype is bf16 and the shape fits (P+L <= 448 fwd), SIMT otherwise;
- * 1 = SIMT kernels only, 2 = tcgen05 kernels but the generic (non-pipelined) backward (A/B testing),
- * 3 = 2 plus the EXPERIMENTAL tcgen05 backward for 128 < L <= 256 (attention_tc_bwd_long.cu; not yet validated on
- *     hardware, never selected by default). */
+/* Same, with a caller-provided workspace (device memory, 256-byte aligned, mtvaf_attention_fwd_workspace_bytes(...)
+ * bytes): long bf16 text whose keys do not fit one resident tile set (P + L > ~400, L <= 512) then runs on tcgen05 as two
+ * key windows + a merge of the partial softmaxes instead of the SIMT kernel.  workspace may be NULL (= mtvaf_attention_fwd). */
+int64_t mtvaf_attention_fwd_workspace_bytes(int B, int L, int nh, int d, int P, int dtype);
+int mtvaf_attention_fwd_ws(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P,
+                        const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx, float* lse,
+                        float* probs, int dtype, float p_drop, uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream);
+/* 0 (default) = tcgen05 kernels whenever dtype is bf16 and the shape fits (L <= 512, P <= 128; forward with P + L beyond
+ *     one resident tile set needs the workspace of mtvaf_attention_fwd_ws), SIMT otherwise;
+ * 1 = SIMT kernels only, 2 = tcgen05 kernels but the generic (non-pipelined) backward for L <= 128 (A/B testing).
+ * Process-global. */
 int mtvaf_set_attention_impl(int impl);
 /* dqkv: [B*L, 3*nh*d]; dkp/dvp: [B, nh, P, d] fp32 gradient of the prefix (may be NULL);
  * dsum_scratch: [B, nh, L] fp32 workspace (rowsum(dO * O)). */

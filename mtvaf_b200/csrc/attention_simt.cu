@@ -482,15 +482,34 @@ using namespace mtvaf;
 static int g_attention_impl = 0;
 namespace mtvaf { int attention_impl_override() { return g_attention_impl; } }
 extern "C" int mtvaf_set_attention_impl(int impl) {
-  MTVAF_REQUIRE(impl >= 0 && impl <= 3,
-                "attention impl must be 0 (auto), 1 (SIMT), 2 (tcgen05, generic backward) or 3 (2 + experimental long-text backward)");
+  MTVAF_REQUIRE(impl >= 0 && impl <= 2,
+                "attention impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05, generic instead of the pipelined backward)");
   g_attention_impl = impl;
   return 0;
+}
+
+// bytes of caller-provided workspace mtvaf_attention_fwd_ws needs for this shape (0 for most: only long bf16 text whose
+// keys do not fit one resident-key tile set -- P + L > ~400 -- runs as two key windows + a merge)
+extern "C" int64_t mtvaf_attention_fwd_workspace_bytes(int B, int L, int nh, int d, int P, int dtype) {
+  if (dtype != MTVAF_BF16 || d != 64 || L <= 256 || L > 512) return 0;
+  AttnTcArgs ta;
+  ta.P = P; ta.P8 = (P + 7) / 8 * 8; ta.L = L; ta.L64 = (L + 63) / 64 * 64; ta.N16 = (ta.P8 + L + 15) / 16 * 16;
+  ta.Lk = L; ta.kt0 = 0; ta.kbase = P; ta.B = B; ta.nh = nh;
+  if (attn_fwd_tc_fits(ta) || !attn_fwd_tc_windows_supported(ta)) return 0;
+  return (int64_t)attn_fwd_tc_windows_workspace(B, L, nh);
 }
 
 extern "C" int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P,
                                    const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx,
                                    float* lse, float* probs, int dtype, float p_drop, uint64_t seed, void* stream) {
+  return mtvaf_attention_fwd_ws(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, d, ctx, ld_ctx, lse, probs, dtype, p_drop,
+                                seed, nullptr, 0, stream);
+}
+
+extern "C" int mtvaf_attention_fwd_ws(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P,
+                                      const int64_t* key_mask, int B, int L, int nh, int d, void* ctx, int64_t ld_ctx,
+                                      float* lse, float* probs, int dtype, float p_drop, uint64_t seed,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
   AttnArgs a;
   if (int rc = fill_args(&a, qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, d, p_drop, seed, dtype)) return rc;
   MTVAF_REQUIRE(ctx && lse, "attention_fwd: null output");
@@ -503,8 +522,14 @@ extern "C" int mtvaf_attention_fwd(const void* qkv, int64_t ld_qkv, const void* 
     AttnTcMaps tm;
     bool ok = false;
     if (int rc = attn_tc_prepare(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, p_drop, seed, &ta, &tm, &ok)) return rc;
-    if (ok) {
+    if (ok && attn_fwd_tc_fits(ta)) {
       if (int rc = attn_fwd_tc_launch(ta, tm, ctx, ld_ctx, lse, st)) return rc;
+      done = true;
+    } else if (ok && attn_fwd_tc_windows_supported(ta) && workspace &&
+               workspace_bytes >= (int64_t)attn_fwd_tc_windows_workspace(B, L, nh) &&
+               (reinterpret_cast<uintptr_t>(workspace) & 255) == 0) {
+      // long text: the keys of an item do not fit -> two key windows through the same kernel, then a merge
+      if (int rc = attn_fwd_tc_windows_launch(ta, tm, ctx, ld_ctx, lse, workspace, st)) return rc;
       done = true;
     }
   }
@@ -550,7 +575,7 @@ extern "C" int mtvaf_attention_bwd_ex(const void* dctx, int64_t ld_dctx, const v
       if (int rc = attn_bwd_tc_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st)) return rc;
       return d_bias_qkv ? mtvaf_colsum(dqkv, ld_dqkv, dtype, B * L, 3 * nh * d, d_bias_qkv, stream) : 0;
     }
-    if (ok && attention_impl_override() == 3 && attn_bwd_long_supported(ta)) {      // experimental, opt-in only
+    if (ok && attn_bwd_long_supported(ta)) {                                        // 128 < L <= 512
       if (int rc = attn_bwd_long_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, st)) return rc;
       return d_bias_qkv ? mtvaf_colsum(dqkv, ld_dqkv, dtype, B * L, 3 * nh * d, d_bias_qkv, stream) : 0;
     }

@@ -16,6 +16,7 @@
 //   store: O / rowsum -> ctx (heads merged, :276-278; 64 B per thread), lse = max + log(rowsum) for backward.
 // The backward kernel (same tiling, five MMAs) is in attention_tc_bwd.cu.
 #include "attention_tc.cuh"
+#include <algorithm>
 
 namespace mtvaf {
 using namespace ptx;
@@ -77,14 +78,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_arrive_expect_tx(&bars[0], 16384u + (uint32_t)key_rows * 128u);
     tma_load_2d(sQ, &tmQ, &bars[0], h * 64, b * a.L + qt * 128);
     for (int r = 0; r < a.P8; r += 8) tma_load_2d(sK + r * 128, &tmKp, &bars[0], 0, (b * a.nh + h) * a.P + r);
-    for (int r = 0; r < a.L64; r += 64) tma_load_2d(sK + (a.P8 + r) * 128, &tmKV, &bars[0], H + h * 64, b * a.L + r);
+    for (int r = 0; r < a.L64; r += 64)
+      tma_load_2d(sK + (a.P8 + r) * 128, &tmKV, &bars[0], H + h * 64, b * a.L + a.kt0 + r);
   };
   auto issue_v = [&](int item) {                     // one thread
     const int bh = item / q_tiles;
     const int b = bh / a.nh, h = bh - b * a.nh;
     mbar_arrive_expect_tx(&bars[3], (uint32_t)key_rows * 128u);
     for (int r = 0; r < a.P8; r += 8) tma_load_2d(sV + r * 128, &tmVp, &bars[3], 0, (b * a.nh + h) * a.P + r);
-    for (int r = 0; r < a.L64; r += 64) tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, &bars[3], 2 * H + h * 64, b * a.L + r);
+    for (int r = 0; r < a.L64; r += 64)
+      tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, &bars[3], 2 * H + h * 64, b * a.L + a.kt0 + r);
   };
   if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
 
@@ -99,7 +102,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (k >= a.N16) return 0.f;
     if (k < a.P8) return (k < a.P) ? 0.f : -INFINITY;
     const int t = k - a.P8;
-    return (t < a.L) ? (a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kFwdLog2e) : -INFINITY;
+    return (t < a.Lk) ? (a.key_mask[(long long)b * a.L + a.kt0 + t] != 0 ? 0.f : -10000.0f * kFwdLog2e) : -INFINITY;
   };
   float mask_next[2] = {0.f, 0.f};
   if ((int)blockIdx.x < n_items) {
@@ -182,7 +185,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         p[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sc2, mk[j] - mxs));
         sum += p[j];
       }
-      if (a.drop_thr) attn_drop_apply8(rowkey, c < a.P8 ? c : a.P + (c - a.P8), a.drop_thr, p);
+      if (a.drop_thr) attn_drop_apply8(rowkey, c < a.P8 ? c : a.kbase + (c - a.P8), a.drop_thr, p);
       uint4 w;
       w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
       w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
@@ -282,12 +285,81 @@ int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int6
   return 0;
 }
 
+bool attn_fwd_tc_fits(const AttnTcArgs& a) { return a.N16 <= 448 && attn_fwd_tc_smem(a) <= 227 * 1024; }
+
+// ---- long text: two key windows + merge -----------------------------------------------------------------------------
+// softmax over the union of two key sets from the two partial results: with lse_i = log sum_{k in window i} exp(s_k),
+//   lse = log(exp(lse_0) + exp(lse_1)),   O = exp(lse_0 - lse) O_0 + exp(lse_1 - lse) O_1
+// (dropout sits in the numerators O_i only, so the merge is unaffected).  One thread per (token, head, 8 columns).
+__global__ void __launch_bounds__(256)
+attn_merge_windows_kernel(__nv_bfloat16* __restrict__ ctx, long long ld_ctx, float* __restrict__ lse,
+                          const __nv_bfloat16* __restrict__ ctx1, const float* __restrict__ lse1, int B, int L, int nh) {
+  const long long n = (long long)B * L * nh * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i & 7);
+    const long long th = i >> 3;
+    const int h = (int)(th % nh);
+    const long long t = th / nh;                       // token = b * L + q
+    const long long b = t / L, q = t - b * L;
+    const long long li = (b * nh + h) * L + q;
+    const float l0 = lse[li], l1 = lse1[li];
+    const float mx = fmaxf(l0, l1);
+    const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx);
+    const float inv = 1.f / (e0 + e1);
+    const float w0 = e0 * inv, w1 = e1 * inv;
+    __nv_bfloat16* o = ctx + t * ld_ctx + h * 64 + v * 8;
+    const __nv_bfloat16* o1 = ctx1 + (t * nh + h) * 64 + v * 8;
+    float a0[8], a1[8];
+    Vec8<__nv_bfloat16>::load(o, a0);
+    Vec8<__nv_bfloat16>::load(o1, a1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = fmaf(w0, a0[j], w1 * a1[j]);
+    Vec8<__nv_bfloat16>::store(o, a0);
+    if (v == 0) lse[li] = mx + __logf(e0 + e1);
+  }
+}
+
+static AttnTcArgs window_args(const AttnTcArgs& a, int w) {
+  AttnTcArgs x = a;
+  constexpr int kWin = 256;                            // text keys per window
+  if (w == 0) { x.kt0 = 0; x.Lk = a.L < kWin ? a.L : kWin; x.kbase = a.P; }
+  else { x.P = 0; x.P8 = 0; x.kt0 = kWin; x.Lk = a.L - kWin; x.kbase = a.P + kWin; }
+  x.L64 = (x.Lk + 63) / 64 * 64;
+  x.N16 = (x.P8 + x.Lk + 15) / 16 * 16;
+  return x;
+}
+
+bool attn_fwd_tc_windows_supported(const AttnTcArgs& a) {
+  if (a.L <= 256 || a.L > 512 || a.P8 > 128) return false;
+  return attn_fwd_tc_fits(window_args(a, 0)) && attn_fwd_tc_fits(window_args(a, 1));
+}
+
+size_t attn_fwd_tc_windows_workspace(int B, int L, int nh) {
+  const size_t ctx1 = ((size_t)B * L * nh * 64 * sizeof(__nv_bfloat16) + 255) / 256 * 256;
+  return ctx1 + (size_t)B * nh * L * sizeof(float);
+}
+
+int attn_fwd_tc_windows_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int64_t ld_ctx, float* lse,
+                               void* workspace, cudaStream_t st) {
+  const size_t ctx1_bytes = ((size_t)a.B * a.L * a.nh * 64 * sizeof(__nv_bfloat16) + 255) / 256 * 256;
+  __nv_bfloat16* ctx1 = reinterpret_cast<__nv_bfloat16*>(workspace);
+  float* lse1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ctx1_bytes);
+  if (int rc = attn_fwd_tc_launch(window_args(a, 0), m, ctx, ld_ctx, lse, st)) return rc;
+  if (int rc = attn_fwd_tc_launch(window_args(a, 1), m, ctx1, (int64_t)a.nh * 64, lse1, st)) return rc;
+  const long long n = (long long)a.B * a.L * a.nh * 8;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  attn_merge_windows_kernel<<<grid, 256, 0, st>>>((__nv_bfloat16*)ctx, ld_ctx, lse, ctx1, lse1, a.B, a.L, a.nh);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
 // shape gate + tensor maps shared by forward and backward
 int attn_tc_prepare(const void* qkv, int64_t ld_qkv, const void* kp, const void* vp, int P, const int64_t* key_mask,
                     int B, int L, int nh, float p_drop, uint64_t seed, AttnTcArgs* a, AttnTcMaps* m, bool* ok) {
   *ok = false;
   a->P = P; a->P8 = (P + 7) / 8 * 8; a->L = L; a->L64 = (L + 63) / 64 * 64;
   a->N16 = (a->P8 + L + 15) / 16 * 16;
+  a->Lk = L; a->kt0 = 0; a->kbase = P;
   a->B = B; a->nh = nh; a->key_mask = reinterpret_cast<const long long*>(key_mask);
   a->scale = 0.125f;
   a->drop_thr = 0; a->drop_scale = 1.f; a->seed = seed; a->step = step_source();
@@ -296,8 +368,9 @@ int attn_tc_prepare(const void* qkv, int64_t ld_qkv, const void* kp, const void*
     a->drop_thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
     a->drop_scale = 1.f / (1.f - p_drop);
   }
-  if (a->N16 > 448 || ld_qkv % 8 != 0 || (reinterpret_cast<uintptr_t>(qkv) & 15)) return 0;
-  if (attn_fwd_tc_smem(*a) > 227 * 1024) return 0;
+  // (whether all keys of an item fit the resident-key kernels is the callers' question: attn_fwd_tc_fits,
+  //  attn_bwd_*_supported; the tensor maps below serve every tcgen05 attention kernel)
+  if (ld_qkv % 8 != 0 || (reinterpret_cast<uintptr_t>(qkv) & 15)) return 0;
   const uint64_t T = (uint64_t)B * L;
   const uint64_t W = 3ull * nh * 64;
   int rc = make_tmap_bf16_2d(&m->q, qkv, W, T, ld_qkv, 64, 128);

@@ -9,8 +9,10 @@ namespace mtvaf {
 
 struct AttnTcArgs {
   int P, P8;            // prefix rows, padded to a multiple of 8 in the shared-memory key numbering
-  int L, L64;           // text rows, padded to a multiple of 64 (TMA box rows)
-  int N16;              // keys covered by the MMAs: round16(P8 + L)
+  int L, L64;           // text rows (queries == keys of the whole item); L64 = text KEY rows loaded, padded to 64
+  int N16;              // keys covered by the MMAs: round16(P8 + Lk)
+  int Lk, kt0, kbase;   // forward key WINDOW: Lk text keys starting at text row kt0; kbase = reference key number of
+                        // the window's first text key (P_total + kt0, dropout hash).  Whole item: Lk = L, kt0 = 0, kbase = P
   int B, nh;
   const long long* key_mask;
   float scale;
@@ -29,6 +31,12 @@ int attn_tc_prepare(const void* qkv, int64_t ld_qkv, const void* kp, const void*
                     int B, int L, int nh, float p_drop, uint64_t seed, AttnTcArgs* a, AttnTcMaps* m, bool* ok);
 int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int64_t ld_ctx, float* lse,
                        cudaStream_t st);
+bool attn_fwd_tc_fits(const AttnTcArgs& a);        // all keys of an item resident (N16 <= 448 and shared memory)
+// long text (P8 + L > what fits): two key windows through the same kernel + a merge of the partial softmaxes
+bool attn_fwd_tc_windows_supported(const AttnTcArgs& a);
+size_t attn_fwd_tc_windows_workspace(int B, int L, int nh);
+int attn_fwd_tc_windows_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int64_t ld_ctx, float* lse,
+                               void* workspace, cudaStream_t st);
 bool attn_bwd_tc_supported(const AttnTcArgs& a);
 int attn_bwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                        int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
@@ -39,7 +47,7 @@ bool attn_bwd_pipe_supported(const AttnTcArgs& a);
 int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                          int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
                          float* dbias, cudaStream_t st);
-// EXPERIMENTAL long-text backward (128 < L <= 256), attention_tc_bwd_long.cu: selected only by impl override 3
+// long-text backward (128 < L <= 512), attention_tc_bwd_long.cu
 bool attn_bwd_long_supported(const AttnTcArgs& a);
 int attn_bwd_long_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                          int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,

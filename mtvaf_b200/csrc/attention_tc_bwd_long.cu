@@ -1,18 +1,19 @@
-// EXPERIMENTAL (opt-in, mtvaf_set_attention_impl(3)): backward of the prefix ("fusion") self-attention on tcgen05 for
-// LONG text, 128 < L <= 256 (the roberta-large / long-auxiliary-text config), any P <= 128.  Written at the end of
-// round 1 WITHOUT GPU time left to run it: the default dispatch does not select it, the SIMT kernels keep serving these
-// shapes (20-40x slower per token, profiles/r1_sweep_partial.md) until this one has been validated.
+// Backward of the prefix ("fusion") self-attention on tcgen05 for LONG text, 128 < L <= 512 (the roberta-large /
+// long-auxiliary-text config and the reference's `--use_align` inputs of up to 500 tokens, MTVAF_training.py:250), any
+// P <= 128.
 //
 // Same math as attention_tc_bwd.cu (flash-attention backward with the saved log-sum-exp,
 // models/modeling_roberta.py:218-278); what differs is the blocking.  One CTA (512 threads) per (batch, head) item:
-//   * both 128-query tiles of Q and dO stay resident in shared memory for the whole item;
-//   * the keys are walked in BLOCKS of <= 128: block 0 = the visual prefix (P8 rows), blocks 1.. = 128 text keys each;
-//     K / V of one block at a time (single-buffered: correctness first);
+//   * the 128-query tiles are processed in GROUPS of two: Q and dO of a group stay resident in shared memory;
+//   * per group the keys are walked in BLOCKS of <= 128: block 0 = the visual prefix (P8 rows), blocks 1.. = 128 text
+//     keys each; K / V of one block at a time;
 //   * per (key block, query tile): S = Q K^T and dP = dO V^T (128 x NB each) -> SIMT softmax -> bf16 P / dS in shared
 //     memory -> dQ[tile] += dS K, dK[block] += dS^T Q, dV[block] += P^T dO;
 //   * TMEM (512 columns): S [0,128) | dP [128,256) | dQ tile 0 [256,320) | dQ tile 1 [320,384) | dK [384,448) |
-//     dV [448,512): dQ accumulates over the key blocks, dK / dV over the query tiles; nothing needs atomics.
-// Every step is separated by block barriers (no overlap between SIMT and MMA phases yet).
+//     dV [448,512): dQ accumulates over the key blocks (final when its group ends), dK / dV over the query tiles of
+//     the group.  With more than one group (L > 256) the later groups ADD their dK / dV to what the same thread of the
+//     same CTA stored before (bf16 text rows, fp32 prefix rows): no atomics, no scratch buffer.
+// Every step is separated by block barriers (no overlap between SIMT and MMA phases).
 #include "attention_tc.cuh"
 
 namespace mtvaf {
@@ -36,7 +37,7 @@ __host__ __device__ inline LongSmem long_layout() {
   s.off_do = o; o += 2 * 16384;
   s.off_k = o;  o += 16384;              // one key block
   s.off_v = o;  o += 16384;
-  s.off_mask = o; o += 3 * 128 * sizeof(float);   // [block][key in block], additive mask * log2(e)
+  s.off_mask = o; o += 5 * 128 * sizeof(float);   // [block][key in block], additive mask * log2(e); <= 1 + 4 blocks
   s.off_lse = o;  o += 256 * sizeof(float);
   s.off_d = o;    o += 256 * sizeof(float);
   s.off_exch = o; o += 4 * 128 * sizeof(float);
@@ -82,8 +83,9 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int row = quad * 32 + lane;                    // query row in its tile == key row in its block == TMEM lane
   const int H = a.nh * 64;
   const int n_items = a.B * a.nh;
-  const int nq = (a.L + 127) / 128;                    // query tiles (<= 2)
-  const int nt = nq;                                   // text key blocks
+  const int nq_all = (a.L + 127) / 128;                // query tiles (<= 4)
+  const int nt = nq_all;                               // text key blocks
+  const int n_groups = (nq_all + 1) / 2;               // query-tile groups of two
   const int n_blocks = nt + (a.P8 > 0 ? 1 : 0);
   const int first_text = a.P8 > 0 ? 1 : 0;
 
@@ -116,19 +118,21 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
   const float ds_coef = a.scale / a.drop_scale;        // dS = P' * (scale / drop_scale) * (dP' - D)
 
-  uint32_t n_kv = 0, n_step = 0;                       // completed phases of bar_kv / (bar_s, bar_g): same in every thread
-  int il = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++il) {
+  uint32_t n_kv = 0, n_step = 0, n_q = 0;              // completed phases of bar_kv / (bar_s, bar_g) / bar_q: same in every thread
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int b = item / a.nh, h = item - b * a.nh;
-    // ---- item prologue: Q / dO tiles by TMA; key masks, log-sum-exp and D_q = rowsum(dO o O) into shared memory
+   for (int qg = 0; qg < n_groups; ++qg) {
+    const int q0 = qg * 256;                             // first query row of the group
+    const int nq = min(2, nq_all - qg * 2);              // query tiles in this group
+    // ---- group prologue: Q / dO tiles by TMA; key masks, log-sum-exp and D_q = rowsum(dO o O) into shared memory
     if (tid == 0) {
       mbar_arrive_expect_tx(bar_q, (uint32_t)nq * 2u * 16384u);
       for (int qt = 0; qt < nq; ++qt) {
-        tma_load_2d(sQ + qt * 16384, &tmQ, bar_q, h * 64, b * a.L + qt * 128);
-        tma_load_2d(sdO + qt * 16384, &tmdO, bar_q, h * 64, b * a.L + qt * 128);
+        tma_load_2d(sQ + qt * 16384, &tmQ, bar_q, h * 64, b * a.L + q0 + qt * 128);
+        tma_load_2d(sdO + qt * 16384, &tmdO, bar_q, h * 64, b * a.L + q0 + qt * 128);
       }
     }
-    for (int k = tid; k < n_blocks * 128; k += kLongThreads) {
+    for (int k = tid; qg == 0 && k < n_blocks * 128; k += kLongThreads) {
       const int kb = k >> 7, kk = k & 127;
       float m;
       if (has_prefix && kb == 0) m = (kk < a.P) ? 0.f : -INFINITY;
@@ -139,13 +143,14 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       sMask[k] = m;
     }
     if (tid < 256) {
-      const int q = tid;
+      const int q = q0 + tid;
       // +inf for rows past L: P = exp2(-inf) = 0
-      sLse[q] = (q < a.L) ? lse[((long long)b * a.nh + h) * a.L + q] * kLog2eL - log2_ds : INFINITY;
+      sLse[tid] = (q < a.L) ? lse[((long long)b * a.nh + h) * a.L + q] * kLog2eL - log2_ds : INFINITY;
     }
-    mbar_wait(bar_q, il & 1);
+    mbar_wait(bar_q, n_q & 1);
+    ++n_q;
     for (int qt = 0; qt < nq; ++qt) {
-      const int q = qt * 128 + row;
+      const int q = q0 + qt * 128 + row;
       float acc = 0.f;
       if (q < a.L) {
         const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)b * a.L + q) * ld_ctx + h * 64 + dcol);
@@ -164,7 +169,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       sExch[part * 128 + row] = acc;
       __syncthreads();
-      if (part == 0) sD[q] = (sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row]);
+      if (part == 0) sD[qt * 128 + row] = (sExch[row] + sExch[128 + row]) + (sExch[256 + row] + sExch[384 + row]);
       __syncthreads();
     }
 
@@ -191,7 +196,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       for (int qt = 0; qt < nq; ++qt) {
-        const int q = qt * 128 + row;
+        const int q = q0 + qt * 128 + row;
         if (tid == 0) {
           const uint32_t aQ = smem_u32(sQ + qt * 16384), aK = smem_u32(sK), adO = smem_u32(sdO + qt * 16384),
                          aV = smem_u32(sV);
@@ -209,8 +214,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_commit(bar_s);
         }
         __syncwarp();
-        const float lse2 = sLse[q < 256 ? q : 255];
-        const float dsum = sD[q < 256 ? q : 255];
+        const float lse2 = sLse[qt * 128 + row];
+        const float dsum = sD[qt * 128 + row];
         const uint32_t rowkey =
             a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
         mbar_wait(bar_s, n_step & 1);
@@ -295,6 +300,19 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_ld_wait();
           if (is_text) {
             uint4* o = reinterpret_cast<uint4*>(dqkv + ((long long)b * a.L + tx) * ld_dqkv + (which + 1) * H + h * 64 + dcol);
+            if (qg > 0) {                        // add what this thread stored for the earlier query groups
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const uint4 old = o[v];
+                const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(ow[j]);
+                  r[v * 8 + 2 * j] = __float_as_uint(__uint_as_float(r[v * 8 + 2 * j]) + f.x);
+                  r[v * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(r[v * 8 + 2 * j + 1]) + f.y);
+                }
+              }
+            }
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               uint4 w;
@@ -309,10 +327,15 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (o) {
               o += (((long long)b * a.nh + h) * a.P + ks) * 64 + dcol;
 #pragma unroll
-              for (int v = 0; v < 4; ++v)
-                *reinterpret_cast<float4*>(o + v * 4) =
-                    make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
-                                __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+              for (int v = 0; v < 4; ++v) {
+                float4 acc = make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
+                                         __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+                if (qg > 0) {
+                  const float4 old = *reinterpret_cast<const float4*>(o + v * 4);
+                  acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + v * 4) = acc;
+              }
             }
           }
         }
@@ -323,9 +346,9 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
     }
 
-    // ---- drain dQ of both query tiles
+    // ---- drain dQ of the group's query tiles
     for (int qt = 0; qt < nq; ++qt) {
-      const int q = qt * 128 + row;
+      const int q = q0 + qt * 128 + row;
       uint32_t r[16];
       __syncwarp();
       tmem_ld_32x32b_x16(t_row + LC_DQ + qt * 64 + dcol, r);
@@ -343,10 +366,11 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     }
-    // all TMEM / shared-memory reads of this item done before the next item's loads and MMAs
+    // all TMEM / shared-memory reads of this group done before the next group's / item's loads and MMAs
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+   }
   }
   if (warp == 0) {
     tc_fence_after();
@@ -357,7 +381,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }  // namespace
 
 bool attn_bwd_long_supported(const AttnTcArgs& a) {
-  return a.L > 128 && a.L <= 256 && a.P8 <= 128 && long_layout().total <= 227 * 1024;
+  return a.L > 128 && a.L <= 512 && a.P8 <= 128 && long_layout().total <= 227 * 1024;
 }
 
 int attn_bwd_long_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,

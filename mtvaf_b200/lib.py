@@ -56,6 +56,8 @@ SIGNATURES = {
     "mtvaf_layernorm_fwd": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp],
     "mtvaf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _u64, _vp],
     "mtvaf_attention_fwd": [_vp, _i64, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _f, _u64, _vp],
+    "mtvaf_attention_fwd_ws": [_vp, _i64, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _f, _u64, _vp,
+                               _i64, _vp],
     "mtvaf_set_attention_impl": [_i],
     "mtvaf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp,
                             _vp, _vp, _i, _f, _u64, _vp],
@@ -97,6 +99,8 @@ def _load():
     lib.mtvaf_last_error.argtypes = []
     lib.mtvaf_launch_count.restype = C.c_uint64
     lib.mtvaf_launch_count.argtypes = []
+    lib.mtvaf_attention_fwd_workspace_bytes.restype = C.c_int64
+    lib.mtvaf_attention_fwd_workspace_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     missing = []
     for name, argtypes in SIGNATURES.items():
         try:

@@ -323,8 +323,7 @@ def embed_ln_bwd(dout, ids, tts, pids, word, pos, typ, gamma, mean, rstd, kind, 
 def set_attention_impl(impl: str):
     """'auto' (tcgen05 kernels when bf16 and the shape fits), 'simt', or 'tc_generic' (tcgen05 kernels with the
     generic instead of the software-pipelined backward) -- A/B testing."""
-    _check(_raw.mtvaf_set_attention_impl({"auto": 0, "simt": 1, "tc_generic": 2, "tc_long_experimental": 3}[impl]),
-           "set_attention_impl")
+    _check(_raw.mtvaf_set_attention_impl({"auto": 0, "simt": 1, "tc_generic": 2}[impl]), "set_attention_impl")
 
 
 def attention_fwd(qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.0, seed=0, want_probs=False):
@@ -333,9 +332,12 @@ def attention_fwd(qkv, kp, vp, key_mask, B, Lq, nh, d, p_drop=0.0, seed=0, want_
     ctx = torch.empty((B * Lq, nh * d), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((B, nh, Lq), dtype=torch.float32, device=qkv.device)
     probs = torch.empty((B, nh, Lq, P + Lq), dtype=torch.float32, device=qkv.device) if want_probs else None
-    _check(_raw.mtvaf_attention_fwd(qkv.data_ptr(), qkv.stride(0), _p(kp), _p(vp), P, key_mask.data_ptr(), B, Lq, nh,
-                                    d, ctx.data_ptr(), ctx.stride(0), lse.data_ptr(), _p(probs), dt(qkv), p_drop,
-                                    seed, _stream()), "attention_fwd")
+    # long text (keys of an item beyond one resident tile set): caller-owned workspace for the two-window forward
+    ws_bytes = int(_raw.mtvaf_attention_fwd_workspace_bytes(B, Lq, nh, d, P, dt(qkv)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device) if ws_bytes > 0 else None
+    _check(_raw.mtvaf_attention_fwd_ws(qkv.data_ptr(), qkv.stride(0), _p(kp), _p(vp), P, key_mask.data_ptr(), B, Lq,
+                                       nh, d, ctx.data_ptr(), ctx.stride(0), lse.data_ptr(), _p(probs), dt(qkv),
+                                       p_drop, seed, _p(ws), ws_bytes, _stream()), "attention_fwd")
     return ctx, lse, probs
 
 

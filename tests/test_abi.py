@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(raw, n), "symbol %s declared in the header but not exported" % n
     # and the ctypes table binds every one of them
     for n in names:
-        if n not in ("mtvaf_last_error", "mtvaf_launch_count"):
+        if n not in ("mtvaf_last_error", "mtvaf_launch_count", "mtvaf_attention_fwd_workspace_bytes"):   # non-int returns
             assert n in lib.SIGNATURES, n
     hdr = open(os.path.join(ROOT, "include", "mtvaf_b200.h")).read()
     assert lib.abi_version() == int(re.search(r"#define MTVAF_ABI_VERSION (\d+)", hdr).group(1)) == 3

@@ -41,7 +41,7 @@ def relrms(a, b):
     return float((a - b).norm() / b.norm())
 
 
-def fit_head(h, labels, mask, lam=0.1):
+def fit_head(h, labels, mask, lam=20.0):
     """Ridge regression of one-hot tags on the fp32 final hidden states: a stand-in for a TRAINED tag head (emission
     margins O(1) instead of the near-ties of a random-init 768->11 projection)."""
     hm = h[mask].double()
@@ -64,7 +64,15 @@ def main():
     vocab = 2000
     from oracle import mtvaf_oracle as O                  # config helper only
     params = S.init_params(O.EncoderCfg.roberta_base(vocab_size=vocab), seed=7, ln_jitter=0.05)
-    batch = {k: v.to(DEV) for k, v in S.make_batch(B, Lq, vocab=vocab, shape="twitter2017", seed=8).items()}
+    cpu_batch = S.make_batch(B, Lq, vocab=vocab, shape="twitter2017", seed=8)
+    if os.environ.get("MTVAF_LEARNABLE_TASK", "1") == "1":
+        # gold tag = function of the token (tests/test_model_gpu.py::_learnable_task_batch): a task a head can learn
+        g = torch.Generator().manual_seed(8 + 99)
+        lab, mask = cpu_batch["labels"], cpu_batch["attention_mask"]
+        width = (vocab - 3) // 11
+        cpu_batch["input_ids"] = (3 + width * (lab - 1).clamp_min(0)
+                                  + torch.randint(0, width, lab.shape, generator=g)) * mask
+    batch = {k: v.to(DEV) for k, v in cpu_batch.items()}
     m32, m16 = build(params, "fp32", vocab), build(params, "bf16", vocab)
     with torch.no_grad():
         kv32, _, _ = m32.get_visual_prompt(batch["images"], batch["aux_imgs"], batch["imagelabel"])
