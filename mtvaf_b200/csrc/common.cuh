@@ -176,12 +176,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
+#ifdef MTVAF_GELU_EXACT      // experiment builds (tools/bf16_error_budget.py): how much of the bf16 error is the tanh form?
+  return gelu_erf(x);
+#endif
   const float x2 = x * x;
   const float t = tanh_approx(x * fmaf(x2, 0.0356774081f, 0.7978845608f));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ float dgelu_fast(float x) {
+#ifdef MTVAF_GELU_EXACT
+  return dgelu_erf(x);
+#endif
   const float x2 = x * x;
   const float t = tanh_approx(x * fmaf(x2, 0.0356774081f, 0.7978845608f));
   const float du = fmaf(x2, 0.1070322243f, 0.7978845608f);      // d/dx of the tanh argument

@@ -1000,22 +1000,33 @@ class TVNetSAModel(nn.Module):
 
     def extraction(self, prompt_attention_mask, input_ids, prefix_guids, token_type_ids, augument=False, labels=None,
                    adj_matrix=None, src_mask=None, aspect_mask=None):
-        """models/bert_model.py:323-361, inference form (no autograd through this entry point: the trainer calls it
-        to propose spans, modules/train.py:362-380; training goes through forward()).  `prompt_attention_mask` is
-        [B, P+L] as in the reference; the text part is its last L columns."""
+        """models/bert_model.py:323-361: span proposals (start / end logits) for the trainer (modules/train.py:362-380).
+        `prompt_attention_mask` is [B, P+L] as in the reference; the text part is its last L columns.
+
+        Default: inference form -- the trainer discards this pass's autograd graph anyway (it detaches the logits,
+        modules/train.py:384-386) and calls forward() for the loss, i.e. the reference runs the encoder twice per
+        step.  With `args.reuse_extraction = True` (opt-in) this pass KEEPS its graph and its
+        activations, and the forward() that follows on the same inputs continues from them instead of recomputing
+        the visual prompt and the encoder: one encoder forward per step instead of two.  The only behavioural
+        difference: both passes then share one dropout draw instead of two independent ones."""
         if augument:
             raise L.MtvafError("Cutoff augmentation is outside the hot path (SURVEY.md 2, row 12)")
         eng = self.engine()
         eng.prepare()
         B, Lq = input_ids.shape
         text_mask = prompt_attention_mask[:, -Lq:].to(torch.long).contiguous()
-        with torch.no_grad():
+        reuse = bool(getattr(self.args, "reuse_extraction", False))
+        self._stash = None
+        with torch.set_grad_enabled(reuse and torch.is_grad_enabled()):
             out = self._encode(input_ids, text_mask, token_type_ids, prefix_guids)
             hs = out["hidden_states"]
+        if reuse:
+            self._stash = dict(key=self._stash_key(input_ids, token_type_ids, text_mask), hs=hs)
+        with torch.no_grad():
             nl = self.bert.config.num_hidden_layers
             use_probe = bool(getattr(self.args, "use_probe", False))
             H = eng.cfg.H
-            hsd = {nl: hs[nl].reshape(B * Lq, H), min(7, nl): hs[min(7, nl)].reshape(B * Lq, H)}
+            hsd = {nl: hs[nl].detach().reshape(B * Lq, H), min(7, nl): hs[min(7, nl)].detach().reshape(B * Lq, H)}
             o, _ = eng.span_heads_fwd(hsd, B, Lq, text_mask, {}, use_probe, float(getattr(self.args, "beta", 0.5)),
                                       int(getattr(self.args, "num_epochs", 30)), self.training, False,
                                       probe_layer=min(7, nl))
@@ -1023,6 +1034,12 @@ class TVNetSAModel(nn.Module):
         if use_probe:
             return o["start_logits"], o["end_logits"], seq, o["prob_loss"].view(())
         return o["start_logits"], o["end_logits"], seq
+
+    @staticmethod
+    def _stash_key(input_ids, token_type_ids, text_mask):
+        """Identity of an encoder input: same storage, same contents version, same values of the (small) mask."""
+        tt = None if token_type_ids is None else (token_type_ids.data_ptr(), token_type_ids._version)
+        return (input_ids.data_ptr(), input_ids._version, tuple(input_ids.shape), tt, tuple(text_mask.shape))
 
     def classification(self, span_starts, span_ends, sequence_input, attention_mask):
         """models/bert_model.py:363-376, inference form: (logits [B,M,4], ac_logits [B*M,4])."""
@@ -1060,10 +1077,15 @@ class TVNetSAModel(nn.Module):
         eng._nested = True
         try:
             a = self.args
-            kv = self.get_visual_prompt(images, aux_imgs) if a.use_prefix else None
             mask = attention_mask.to(torch.long).contiguous()
-            out = self._encode(input_ids, mask, token_type_ids, kv)
-            hs = out["hidden_states"]
+            stash, self._stash = getattr(self, "_stash", None), None
+            if stash is not None and stash["key"] == self._stash_key(input_ids, token_type_ids, mask) and \
+                    (stash["hs"][0].requires_grad or not torch.is_grad_enabled()):
+                # args.reuse_extraction: continue from the activations (and autograd graph) of the extraction() pass
+                hs = stash["hs"]
+            else:
+                kv = self.get_visual_prompt(images, aux_imgs) if a.use_prefix else None
+                hs = self._encode(input_ids, mask, token_type_ids, kv)["hidden_states"]
             nl = self.bert.config.num_hidden_layers
             use_probe = bool(getattr(a, "use_probe", False))
             lab = lambda t: None if t is None else t.to(torch.long).contiguous()

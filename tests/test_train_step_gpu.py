@@ -113,7 +113,8 @@ def test_graph_replays_equal_eager_steps_with_dropout(dtype):
           % (dtype, g_losses, worst_w, who, worst_u))
     # bf16: a 1e-7 difference in a weight (atomics order) can flip the bf16 rounding of its shadow, which the next
     # forward amplifies to O(1e-3) gradient differences; the head runs at lr 5e-2 (measured: fc.weight 1.7e-3)
-    assert worst_w < (1e-5 if dtype == "fp32" else 5e-3), (who, worst_w)
+    # fp32: atomics-order noise in the head gradients, amplified by Adam at lr 5e-2 (measured: fc.bias <= 2e-5)
+    assert worst_w < (1e-4 if dtype == "fp32" else 5e-3), (who, worst_w)
     assert worst_u < (2e-2 if dtype == "fp32" else 0.2), worst_u
     assert float((m_g - oe.m).norm() / oe.m.norm()) < (1e-4 if dtype == "fp32" else 2e-2)
     # a dropped GraphedTrainStep must not leave its step counter registered (dangling raw pointer)

@@ -133,13 +133,15 @@ def cell(Lq, P, iters, flush):
     return r
 
 
-def fusion(iters, flush):
-    """get_visual_prompt at the reference shape: 1 image + 3 aux crops, pyramid features [B, 3840, 2, 2]."""
+def fusion(iters, flush, n_img=4):
+    """get_visual_prompt at the reference shape (1 image + 3 aux crops) or with the full image only (n_img = 1):
+    pyramid features [B, 3840, 2, 2], forward and forward+backward."""
     from transformers import RobertaConfig
     from mtvaf_b200.modules import TVNetSAModel2, FeatureStub
     B = 256
     args = SimpleNamespace(bert_name="roberta-base", prefix_dim=768, prefix_len=4, use_prefix=True, use_probe=True,
-                           beta=0.5, alpha=0.1, vao=True, noauxloss=False, resnet_root=None, compute_dtype="bf16", n_gpu=1)
+                           beta=0.5, alpha=0.1, vao=True, noauxloss=False, resnet_root=None, compute_dtype="bf16", n_gpu=1,
+                           probe_ckpt="")
     cfg = RobertaConfig(vocab_size=4096, hidden_size=H, num_hidden_layers=12, num_attention_heads=NH,
                         intermediate_size=4 * H, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5,
                         pad_token_id=1)
@@ -147,14 +149,43 @@ def fusion(iters, flush):
     m = TVNetSAModel2(list(range(10)), None, args, config=cfg, image_model=FeatureStub()).to(DEV).eval()
     g = torch.Generator(device=DEV).manual_seed(5)
     images = torch.randn(B, 3840, 2, 2, device=DEV, generator=g).abs()
-    aux = torch.randn(B, 3, 3840, 2, 2, device=DEV, generator=g).abs()
+    aux = torch.randn(B, 3, 3840, 2, 2, device=DEV, generator=g).abs() if n_img > 1 else None
     label = torch.softmax(torch.randn(B, 2089, device=DEV, generator=g), -1)
 
     def f():
         with torch.no_grad():
             m.get_visual_prompt(images, aux, label)
 
-    return {"B": B, "n_img": 4, "visual_prompt_fwd_us": timeit(f, iters, flush)}
+    def fb():
+        kv, l0, laux = m.get_visual_prompt(images, aux, label)
+        (kv.float().sum() * 1e-3 + l0 + sum(laux)).backward()
+
+    fl = B * n_img * (4 * 2.0 * (3840 * 800 + 800 * 8 * H) + 12 * 2.0 * 8 * H * 4 + 2.0 * 8 * H * 2089)
+    r = {"B": B, "n_img": n_img, "visual_prompt_fwd_us": timeit(f, iters, flush)}
+    r["visual_prompt_fwd_tflops"] = fl / r["visual_prompt_fwd_us"] / 1e6
+    m.train()
+    r["visual_prompt_fb_us"] = timeit(fb, iters, flush)
+    r["visual_prompt_fb_tflops"] = 3 * fl / r["visual_prompt_fb_us"] / 1e6
+    return r
+
+
+def to_markdown(res):
+    rows = ["| L | P | B | attn fwd | attn bwd | attn fwd TF/s | attn bwd TF/s | 1 layer fwd | 1 layer fwd+bwd | layer f+b TF/s | "
+            "us per 1k tokens (layer f+b) | OneWord probe (layers 4 / 7: same shape) | TwoWord probe |",
+            "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for c in res["cells"]:
+        g = lambda k, f="%.0f": (f % c[k]) if k in c else "-"
+        per1k = ("%.1f" % (c["layer_fb_us"] / (c["B"] * c["L"] / 1000.0))) if "layer_fb_us" in c else "-"
+        rows.append("| %d | %d | %d | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
+            c["L"], c["P"], c["B"], g("attn_fwd_us"), g("attn_bwd_us"), g("attn_fwd_tflops"), g("attn_bwd_tflops"),
+            g("layer_fwd_us"), g("layer_fb_us"), g("layer_fb_tflops"), per1k, g("probe_one_us"), g("probe_two_us")))
+    out = ["# configs[4] sweep -- `python tools/bench_sweep.py`, T = %d tokens per cell, bf16, us per call (median, L2 flushed)"
+           % res["tokens_per_cell"], ""] + rows + [""]
+    for f in res.get("fusion", []):
+        out.append("Visual-prompt stack (`get_visual_prompt`, B=%d, n_img=%d): forward %.0f us (%.0f TF/s), forward+backward "
+                   "%.0f us (%.0f TF/s)." % (f["B"], f["n_img"], f["visual_prompt_fwd_us"], f["visual_prompt_fwd_tflops"],
+                                             f["visual_prompt_fb_us"], f["visual_prompt_fb_tflops"]))
+    return "\n".join(out) + "\n"
 
 
 def main():
@@ -171,13 +202,16 @@ def main():
             c = cell(Lq, P, a.iters, flush)
             print(json.dumps(c), flush=True)
             res["cells"].append(c)
-    try:
-        res["fusion"] = fusion(a.iters, flush)
-        print(json.dumps(res["fusion"]), flush=True)
-    except Exception as e:
-        res["fusion_error"] = repr(e)
+    res["fusion"] = []
+    for n_img in (1, 4):
+        try:
+            res["fusion"].append(fusion(a.iters, flush, n_img))
+            print(json.dumps(res["fusion"][-1]), flush=True)
+        except Exception as e:
+            res["fusion_error_%d" % n_img] = repr(e)
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     json.dump(res, open(a.out, "w"), indent=1)
+    open(os.path.splitext(a.out)[0] + ".md", "w").write(to_markdown(res))
 
 
 if __name__ == "__main__":
