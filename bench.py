@@ -617,7 +617,7 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         dp_check = {"weights_equal": bool(torch.equal(lo[:2], hi[:2])), "adam_m_equal": bool(lo[2] == hi[2]),
                     "checksum": float(lo[0]), "max_rank_spread": float((hi - lo).abs().max()),
-                    "steps_checked": int(opt.t), "synced": dp_debug != "nosync"}
+                    "steps_checked": int(opt.dyn[0]) if opt.dyn is not None else int(opt.t), "synced": dp_debug != "nosync"}
 
     if rank == 0:
         fl = flops_per_sample(w, train=train)
