@@ -30,6 +30,7 @@ def main():
         if not any(c[k] for k in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM")):
             continue
         name = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.strip() or fn
+        name = name.replace("(anonymous namespace)::", "")
         rows.append((re.sub(r"\(.*", "", name)[:110], c))
         tot.update(c)
     rows.sort(key=lambda r: -r[1]["UTCHMMA"])
