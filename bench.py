@@ -316,7 +316,7 @@ def name_gemm(w, B, key):
                 (T, H, H // 2): "probe_dgrad"}.get((M, N, K))
     elif (a_mn, b_mn) == (0, 1):
         role = {(T, H, 3 * H): "qkv_dgrad_resid", (T, H, H): "attn_out_dgrad", (T, H, I): "ffn1_dgrad_resid",
-                (T, I, H): "ffn2_dgrad_dgelu_colsum", (T, H // 2, H): "probe_fwd_sqnorm",
+                (T, I, H): "ffn2_dgrad_dgelu_colsum", (T, H // 2, H): "probe_fwd",
                 (rows4, 800, 8 * H): "fusion_mlp2_dgrad_dtanh", (B, 8 * H, 2089): "anp_head_dgrad",
                 (T, H, 11): "tag_head_dgrad"}.get((M, N, K))
     elif (a_mn, b_mn) == (1, 1):

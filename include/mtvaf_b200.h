@@ -25,7 +25,7 @@ extern "C" {
 
 #define MTVAF_ABI_VERSION 3   /* 2: MtvafEpilogue.colsum, mtvaf_attention_bwd_ex, mtvaf_set_sm_reserve
                                * 3: mtvaf_set_pairwise_impl, mtvaf_pack_features (tcgen05 TwoWord probe; feature wire format),
-                               *    mtvaf_attention_fwd_ws / _workspace_bytes (long-text tcgen05 attention) */
+                               *    mtvaf_attention_fwd_ws / _workspace_bytes (long-text tcgen05 attention), mtvaf_row_sqnorm */
 #define MTVAF_F32 0
 #define MTVAF_BF16 1
 
@@ -241,6 +241,9 @@ int mtvaf_pack_features(const void* images, int64_t img_ld, const void* aux_imgs
                         int n_aux, int64_t E, void* out, int out_dtype, void* stream);
 
 /* ---- psdProbe: probes/probe.py:74-78, probes/constructLabel.py:11-29, probes/probe_trainModel.py:23-24 */
+/* OneWordPSDProbe probes/probe.py:74-78: out[r] = sum_c x[r][c]^2 over the projected tokens x [rows, cols] (cols % 8 == 0):
+ * the bf16 path stores T = x proj with the TMA-store epilogue and takes the norms from it in one HBM-bound pass. */
+int mtvaf_row_sqnorm(const void* x, int64_t ld, int dtype, int64_t rows, int cols, float* out, void* stream);
 /* bit-exact pseudo labels (stable sort + sequential fp32 scan) for norms [B, L] fp32 -> labels [B, L] fp32 */
 int mtvaf_probe_labels(const float* norms, float* labels, int B, int L, void* stream);
 /* loss[0] = mean((norms-labels)^2) ; dnorms (optional) = 2 (norms-labels) / (B L) */

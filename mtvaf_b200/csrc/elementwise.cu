@@ -494,6 +494,39 @@ extern "C" int mtvaf_adamw_step(float* param, float* grad, float* exp_avg, float
   return 0;
 }
 
+// ---- row squared norms: out[r] = sum_c x[r][c]^2 (OneWordPSDProbe, probes/probe.py:74-78: the degenerate bmm of
+// [T,1,r] x [T,r,1]).  One warp per row, 16-byte loads, shuffle reduction; cols % 8 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_sqnorm_kernel(const T* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const T* p = x + r * ld;
+    float acc = 0.f;
+    for (int c = lane * 8; c < cols; c += 256) {
+      float v[8];
+      Vec8<T>::load(p + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(v[j], v[j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[r] = acc;
+  }
+}
+
+extern "C" int mtvaf_row_sqnorm(const void* x, int64_t ld, int dtype, int64_t rows, int cols, float* out, void* stream) {
+  MTVAF_REQUIRE(x && out && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, "row_sqnorm: bad argument");
+  MTVAF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "row_sqnorm: x must be 16-byte aligned");
+  const int grid = (int)std::min<long long>((rows + 7) / 8, (long long)sm_count() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTVAF_BF16) row_sqnorm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, cols, out);
+  else row_sqnorm_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, cols, out);
+  MTVAF_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- feature wire format: [B, E] + [B, n_aux, E] (fp32 / bf16) -> [1 + n_aux, B, E] (fp32 / bf16), 8 elements per thread
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)

@@ -72,6 +72,15 @@ class FlatParams:
                 order += names
         emb = [n for n in named if n.startswith(enc_prefix + "embeddings.")]
         rest = [n for n in named if n not in set(order) and n not in set(emb)]
+        # the gate projectors (models/bert_model.py:455: one Linear(8H, 4) per layer) are consumed as ONE [4n, 8H] matrix
+        # (+ [4n] bias) by the single gate GEMM: pack their weights, then their biases, contiguously -- no torch.cat
+        # per forward, and their gradients are views of the flat buffer the wgrad kernel accumulates into directly
+        pj_w = [n for n in rest if n.startswith("projectors.") and n.endswith(".weight")]
+        pj_b = [n for n in rest if n.startswith("projectors.") and n.endswith(".bias")]
+        pj_w.sort(key=lambda n: int(n.split(".")[1]))
+        pj_b.sort(key=lambda n: int(n.split(".")[1]))
+        self.projector_names = (pj_w, pj_b)
+        rest = [n for n in rest if n not in set(pj_w) and n not in set(pj_b)] + pj_w + pj_b
         order += rest
         self.n_cast_names = len(order)           # everything before the embedding tables gets a bf16 shadow
         order += emb
@@ -85,7 +94,9 @@ class FlatParams:
             p = named[n]
             tail = n.split("encoder.layer.")[-1].split(".", 1)[-1] if "encoder.layer." in n else ""
             packed = tail in qkv_w or tail in qkv_b      # q,k,v blocks must be exactly adjacent
-            if not (packed and tail not in (_LAYER_ORDER[0], _LAYER_ORDER[3])):
+            follows = packed and tail not in (_LAYER_ORDER[0], _LAYER_ORDER[3])
+            follows = follows or (n in pj_w[1:]) or (n in pj_b[1:])
+            if not follows:
                 off = (off + _ALIGN - 1) // _ALIGN * _ALIGN
             self.offsets[n] = (off, p.numel())
             off += p.numel()
@@ -210,6 +221,8 @@ class Engine:
         except Exception:
             rank = 0
         self.base_seed = ((torch.initial_seed() ^ 0x5EED) + 7919 * rank) & 0x7FFFFFFF
+        self._kv_internal_ptr = None       # prefix tensor handed from the fusion stack to the encoder within one forward
+        self._dkv32: Dict[int, torch.Tensor] = {}
         self.layer_grad_hook: Optional[Callable[[int], None]] = None   # DP: called when layer i's grads are final
         self.tail_grad_hook: Optional[Callable[[], None]] = None       # DP: called when the embedding grads are final
 
@@ -317,7 +330,9 @@ class Engine:
         step = saved["step"]
         sd = lambda site: ((self.base_seed * 1000003 + step) * 4099 + site) & 0xFFFFFFFFFFFFFFFF
         P = 0 if kv is None else kv.shape[3] // H
-        dkv = torch.zeros((c.n_layers, 2, B, P * H), dtype=F32, device=mask.device) if (kv is not None and want_dkv) else None
+        # every layer that runs its attention backward overwrites its whole [2, B, P*H] slice (plain stores): only the
+        # layers no gradient reaches are cleared (600 MB at B=512 otherwise memset per step)
+        dkv = torch.empty((c.n_layers, 2, B, P * H), dtype=F32, device=mask.device) if (kv is not None and want_dkv) else None
         T = B * Lq
 
         def as_cd(t):
@@ -335,6 +350,8 @@ class Engine:
                 # no gradient reaches this layer's output (yet): only an injected grad can start the chain
                 if grad_hs[i] is not None:
                     dy = as_cd(grad_hs[i])
+                if dkv is not None:
+                    dkv[i].zero_()
                 if self.layer_grad_hook:
                     self.layer_grad_hook(i)
                 continue
@@ -440,25 +457,26 @@ class Engine:
             saved.update(gmd=gmd, dlogits=dlogits, names=names, n_anp=n_anp, p_i=p_i, seed_i=self.seed(900))
         gs = ops.mean4_fwd(guids, rows, W8, 1)                                                   # [rows, 8H]
         # all 12 projectors in one skinny GEMM: [rows, 8H] x [n_layers*4, 8H]^T
-        pw, pb = self._projector_pack()
-        gs32 = ops.cast_f32(gs) if gs.dtype == BF16 else gs
+        pw, pb = self._projector_pack(f.W)
         if cd == BF16:
             # tensor cores, no split-K (deterministic): [rows, 8H] x [48, 8H]^T with fp32 logits out
-            pwb = torch.cat([f.wb("projectors.%d.weight" % l) for l in range(c.n_layers)], 0)
+            pwb, _ = self._projector_pack(f.Wb)
             gate_logits = ops.gemm(gs, pwb, M=rows, N=4 * c.n_layers, K=W8, bias=pb, out_dtype=F32)
         else:
-            gate_logits = ops.skinny_linear(gs32, pw, pb)        # [rows, 48], deterministic warp-per-row kernel
+            gate_logits = ops.skinny_linear(gs, pw, pb)          # [rows, 48], deterministic warp-per-row kernel
         kv, gates = ops.gate_fwd(guids, gate_logits, c.n_layers, n_img, B, H)
-        saved.update(gs32=gs32, gate_logits=gate_logits, gates=gates)
+        saved.update(gs=gs, gate_logits=gate_logits, gates=gates)
         return kv, img_losses, (saved if save else None)
 
-    def _projector_pack(self):
-        """projectors[l].weight [4, 8H] / bias [4] are registered interleaved; pack them as one
-        [4*n_layers, 8H] fp32 matrix (+ [4*n_layers] bias) for the single gate GEMM."""
+    def _projector_pack(self, buf: torch.Tensor):
+        """projectors[l].weight [4, 8H] / bias [4] as ONE [4*n_layers, 8H] matrix (+ [4*n_layers] bias): views of the
+        flat buffer `buf` (W, Wb or G) -- FlatParams packs them contiguously in layer order."""
         f, c = self.flat, self.cfg
-        pw = torch.cat([f.w("projectors.%d.weight" % l) for l in range(c.n_layers)], 0)
-        pb = torch.cat([f.w("projectors.%d.bias" % l) for l in range(c.n_layers)], 0)
-        return pw, pb
+        pj_w, pj_b = f.projector_names
+        if len(pj_w) != c.n_layers:
+            raise L.MtvafError("expected %d gate projectors, found %d" % (c.n_layers, len(pj_w)))
+        return (f.span(buf, pj_w[0], pj_w[-1], (4 * c.n_layers, 8 * c.H)),
+                f.span(buf, pj_b[0], pj_b[-1], (4 * c.n_layers,)))
 
     def fusion_bwd(self, saved, dkv: torch.Tensor, d_img_losses: Optional[torch.Tensor]):
         """dkv fp32 [n_layers,2,B,P*H]; d_img_losses: device fp32 [n_img] weights of the ANP losses."""
@@ -471,16 +489,20 @@ class Engine:
         d_guids = torch.empty((rows4, W8), dtype=F32, device=guids.device)      # written by gate_bwd
         d_gate_logits = ops.gate_bwd(dkv, guids, saved["gate_logits"], saved["gates"], c.n_layers, n_img, B, H,
                                      d_guids)
-        # projector GEMM backward (fp32 skinny)
-        pw, pb = self._projector_pack()
-        dpw = torch.zeros_like(pw)
-        dpb = torch.zeros_like(pb)
-        ops.linear_wgrad(d_gate_logits, saved["gs32"], dpw)
+        # projector GEMM backward: gradients accumulate straight into the packed [4n, 8H] / [4n] views of the flat
+        # gradient buffer (no temporaries, no per-layer scatter)
+        dpw, dpb = self._projector_pack(f.G)
+        gs = saved["gs"]
+        if cd == BF16:
+            dgl = ops.cast_bf16(d_gate_logits)                                                   # [rows, 48]: tiny
+            ops.linear_wgrad(dgl, gs, dpw)                                                       # tcgen05, K = rows
+            pwb, _ = self._projector_pack(f.Wb)
+            d_gs = ops.linear_dgrad(dgl, pwb, out_dtype=F32)                                     # [rows, 8H] fp32
+        else:
+            pw, _ = self._projector_pack(f.W)
+            ops.linear_wgrad(d_gate_logits, gs, dpw)
+            d_gs = ops.linear_dgrad(d_gate_logits, pw)                                           # [rows, 8H] fp32
         ops.colsum(d_gate_logits, dpb)
-        for l in range(c.n_layers):
-            ops.add_inplace(f.g("projectors.%d.weight" % l), dpw[4 * l:4 * l + 4].contiguous())
-            ops.add_inplace(f.g("projectors.%d.bias" % l), dpb[4 * l:4 * l + 4].contiguous())
-        d_gs = ops.linear_dgrad(d_gate_logits, pw)                                               # [rows, 8H] fp32
         d_gmd, p_i, seed_i = None, 0.0, 0
         if saved["vao"] and saved["dlogits"] is not None and d_img_losses is not None:
             dlog = saved["dlogits"]
@@ -541,10 +563,16 @@ class Engine:
             x7 = hs[probe_layer]
             proj = f.params["oneWordpsdProbe.oneWordpsdProbe.proj"]
             r = proj.shape[1]
-            norms = torch.zeros(T, dtype=F32, device=seq.device)
             projc = self.cw("oneWordpsdProbe.oneWordpsdProbe.proj")
-            Tm = torch.empty((T, r), dtype=x7.dtype, device=seq.device)
-            ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H, mode=L.EPI_SQNORM, rowvec=norms, out=Tm)
+            if x7.dtype == BF16 and r % 8 == 0:
+                # T through the TMA-store epilogue, norms from it in one HBM-bound pass (the fused squared-norm epilogue
+                # took 410 us for this 19 GFLOP GEMM: per-thread row stores + one fp32 atomic per 32 columns)
+                Tm = ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H)
+                norms = ops.row_sqnorm(Tm)
+            else:
+                norms = torch.zeros(T, dtype=F32, device=seq.device)
+                Tm = torch.empty((T, r), dtype=x7.dtype, device=seq.device)
+                ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H, mode=L.EPI_SQNORM, rowvec=norms, out=Tm)
             plabels = ops.probe_labels(norms.view(B, Lq))
             prob_loss, dnorms = ops.mse(norms, plabels.view(-1), save)
             out.update(prob_loss=prob_loss, norms=norms.view(B, Lq), pseudo_labels=plabels)
@@ -649,10 +677,14 @@ def _span_heads_fwd(self, hs: List[torch.Tensor], B: int, Lq: int, mask: torch.T
         x7 = hs[probe_layer]
         proj = f.params["oneWordpsdProbe.oneWordpsdProbe.proj"]
         r = proj.shape[1]
-        norms = torch.zeros(T, dtype=F32, device=seq.device)
         projc = self.cw("oneWordpsdProbe.oneWordpsdProbe.proj")
-        Tm = torch.empty((T, r), dtype=x7.dtype, device=seq.device)
-        ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H, mode=L.EPI_SQNORM, rowvec=norms, out=Tm)
+        if x7.dtype == BF16 and r % 8 == 0:
+            Tm = ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H)
+            norms = ops.row_sqnorm(Tm)
+        else:
+            norms = torch.zeros(T, dtype=F32, device=seq.device)
+            Tm = torch.empty((T, r), dtype=x7.dtype, device=seq.device)
+            ops.gemm(x7, projc, b_mn=True, M=T, N=r, K=H, mode=L.EPI_SQNORM, rowvec=norms, out=Tm)
         plabels = ops.probe_labels(norms.view(B, Lq))
         prob_loss, dnorms = ops.mse(norms, plabels.view(-1), save)
         out.update(prob_loss=prob_loss, norms=norms.view(B, Lq), pseudo_labels=plabels)

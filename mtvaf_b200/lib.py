@@ -69,6 +69,7 @@ SIGNATURES = {
     "mtvaf_mean4_fwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "mtvaf_mean4_bwd_add": [_vp, _vp, _i64, _i, _i, _vp],
     "mtvaf_softmax_kl_fwd_bwd": [_vp, _i64, _vp, _i, _i, _i, _vp, _vp, _f, _vp],
+    "mtvaf_row_sqnorm": [_vp, _i64, _i, _i64, _i, _vp, _vp],
     "mtvaf_probe_labels": [_vp, _vp, _i, _i, _vp],
     "mtvaf_mse_fwd_bwd": [_vp, _vp, _i64, _vp, _vp, _vp],
     "mtvaf_pairwise_sqdist": [_vp, _i64, _i, _i, _i, _i, _vp, _vp],

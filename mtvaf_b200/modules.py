@@ -171,6 +171,12 @@ class _EncoderFn(torch.autograd.Function):
         ctx.engine, ctx.saved = engine, saved
         ctx.kv_grad = kv is not None and kv.requires_grad
         ctx.kv_dtype = None if kv is None else kv.dtype
+        # prefix produced by this model's own fusion stack in the same forward (single consumer): its fp32 gradient is
+        # handed to _FusionFn.backward directly instead of through a bf16 round trip (600 MB each way at B=512)
+        ctx.kv_ptr = None
+        if kv is not None and getattr(engine, "_kv_internal_ptr", None) == kv.data_ptr():
+            ctx.kv_ptr = kv.data_ptr()
+            engine._kv_internal_ptr = None
         ctx.emb_grad = embeds is not None and embeds.requires_grad
         B, Lq = ids.shape
         outs = tuple(h.view(B, Lq, -1) for h in hs)
@@ -187,7 +193,13 @@ class _EncoderFn(torch.autograd.Function):
         dkv, demb = eng.encoder_bwd(ctx.saved, list(grads[:n + 1]), ctx.kv_grad, ctx.emb_grad)
         ctx.saved = None
         if dkv is not None and ctx.kv_dtype == BF16:
-            dkv = ops.cast_bf16(dkv)
+            if ctx.kv_ptr is not None:
+                eng._dkv32[ctx.kv_ptr] = dkv
+                if getattr(eng, "_dummy_bf16", None) is None or eng._dummy_bf16.device != dkv.device:
+                    eng._dummy_bf16 = torch.zeros(1, dtype=BF16, device=dkv.device)
+                dkv = eng._dummy_bf16.expand(dkv.shape)      # placeholder of the right shape / dtype for autograd
+            else:
+                dkv = ops.cast_bf16(dkv)
         # (`embeds` entered as [T, H]; its gradient leaves in the same shape)
         return (None, None, None, None, None, None, demb, None, dkv)
 
@@ -198,6 +210,7 @@ class _FusionFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         kv, img_losses, saved = engine.fusion_fwd(feats, imagelabel, vao, training, need_grad, n_aux_heads)
         ctx.engine, ctx.saved = engine, saved
+        ctx.kv_ptr = kv.data_ptr()
         if img_losses is None:
             img_losses = torch.zeros(feats.shape[0], dtype=F32, device=feats.device)
         return kv, img_losses
@@ -206,6 +219,9 @@ class _FusionFn(torch.autograd.Function):
     def backward(ctx, dkv, dimg):
         eng = ctx.engine
         eng.flat.attach_grads()
+        d32 = eng._dkv32.pop(ctx.kv_ptr, None)               # fp32 gradient handed over by _EncoderFn.backward
+        if d32 is not None:
+            dkv = d32
         if dkv is None:
             dkv = torch.zeros_like(ctx.saved["gates"]).new_zeros(
                 (eng.cfg.n_layers, 2, ctx.saved["B"], 4 * ctx.saved["n_img"] * eng.cfg.H))
@@ -860,6 +876,7 @@ class TVNetSAModel2(nn.Module):
         if a.use_prefix:
             kv, _, _ = self.get_visual_prompt(images, aux_imgs, imagelabel)
             img_losses = self._img_losses
+            eng._kv_internal_ptr = kv.data_ptr()              # consumed once, by the encoder call right below
         out = self.bert(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids,
                         past_key_values=kv, output_attentions=True, output_hidden_states=True, return_dict=True)
         hs = out["hidden_states"]
@@ -1085,6 +1102,8 @@ class TVNetSAModel(nn.Module):
                 hs = stash["hs"]
             else:
                 kv = self.get_visual_prompt(images, aux_imgs) if a.use_prefix else None
+                if kv is not None:
+                    eng._kv_internal_ptr = kv.data_ptr()      # consumed once, by the encoder call right below
                 hs = self._encode(input_ids, mask, token_type_ids, kv)["hidden_states"]
             nl = self.bert.config.num_hidden_layers
             use_probe = bool(getattr(a, "use_probe", False))

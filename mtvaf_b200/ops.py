@@ -405,6 +405,16 @@ def softmax_kl(logits, n, target, B, want_grad, grad_scale=1.0):
     return loss, dlogits
 
 
+def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
+    """out[r] = sum_c x[r, c]^2 (fp32) for a 2-D bf16 / fp32 tensor with cols % 8 == 0."""
+    _cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    _check(_raw.mtvaf_row_sqnorm(x.data_ptr(), x.stride(0), dt(x), x.shape[0], x.shape[1], out.data_ptr(), _stream()),
+           "row_sqnorm")
+    return out
+
+
 def probe_labels(norms):
     B, Lq = norms.shape
     labels = torch.empty_like(norms)

@@ -826,3 +826,13 @@ def test_span_heads_kernels(ops):
     d = ops.ce_mean(lg.detach().to(DEV), y.to(DEV), 1.0, loss, True)
     assert abs(float(loss) - float(F.cross_entropy(lg, y))) < 1e-5
     assert rel_err(d, lg.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_row_sqnorm(ops, dtype):
+    x = rnd(1000, 384, seed=77, dtype=dtype)
+    got = ops.row_sqnorm(x)
+    ref = (x.float().double() ** 2).sum(-1).float()
+    assert rel_err(got, ref) < 1e-6
+    xs = rnd(37, 512, seed=78, dtype=dtype)[:, :128]          # strided rows
+    assert rel_err(ops.row_sqnorm(xs), (xs.float().double() ** 2).sum(-1).float()) < 1e-6
