@@ -112,6 +112,62 @@ __device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t 
   }
 }
 
+// Same math for NG groups of 8 consecutive columns (NG = 2: the 16-column steps of the 16-warp epilogue of the CTA-pair
+// kernel, which keeps its live registers under the 112 a 576-thread CTA allows).  keep: dropout keep bits, bit j = column j.
+template <int MODE, int NG>
+__device__ __forceinline__ void epi_compute_groups(const EpiArgs& ep, const uint32_t (&r)[8 * NG],
+                                                   const float (&bias)[8 * NG], const uint4 (&aux4)[NG], uint32_t keep,
+                                                   uint32_t (&outp)[4 * NG], uint32_t (&prep)[4 * NG]) {
+  constexpr bool needs_aux = StagedEpi<MODE>::kAux;
+  const float alpha = ep.alpha;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float v[8], a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), alpha, bias[g * 8 + j]);
+    if (needs_aux) {
+      const float2 a0 = unpack_bf16x2(aux4[g].x), a1 = unpack_bf16x2(aux4[g].y), a2 = unpack_bf16x2(aux4[g].z),
+                   a3 = unpack_bf16x2(aux4[g].w);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = v[j];
+      if (MODE == MTVAF_EPI_GELU) o[j] = gelu_fast(x);
+      else if (MODE == MTVAF_EPI_TANH) o[j] = tanhf(x);
+      else if (MODE == MTVAF_EPI_RESID)
+        o[j] = ((keep >> (g * 8 + j)) & 1u) ? fmaf(x, ep.drop_scale, a[j]) : a[j];
+      else if (MODE == MTVAF_EPI_MUL_DGELU) o[j] = x * dgelu_fast(a[j]);
+      else if (MODE == MTVAF_EPI_MUL_DTANH) o[j] = x * (1.f - a[j] * a[j]);
+      else o[j] = x;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) outp[g * 4 + j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
+    if (MODE == MTVAF_EPI_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) prep[g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    }
+  }
+}
+
+// bias of 16 consecutive columns into registers
+__device__ __forceinline__ void epi_load_bias16(const EpiArgs& ep, int col0, int N, bool full, float (&b)[16]) {
+  if (ep.bias == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[j] = 0.f;
+  } else if (full) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + g * 4));
+      b[g * 4] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[j] = (col0 + j < N) ? __ldg(ep.bias + col0 + j) : 0.f;
+  }
+}
+
 // byte offset of 16-byte piece `c16` (0..7) of row `row` (0..31) inside a SWIZZLE_128B [32][64 bf16] box
 __device__ __forceinline__ uint32_t box_piece_off(int row, int c16) {
   return static_cast<uint32_t>(row * 128 + ((c16 ^ (row & 7)) << 4));

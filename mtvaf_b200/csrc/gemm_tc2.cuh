@@ -11,12 +11,32 @@
 //   tmem_full[a]  (one per CTA)  : commit multicast -> both CTAs' epilogue warps
 //   tmem_empty[a] (leader only)  : 2 x kEpiWarps arrivals (peer epilogue warps arrive remotely)
 // Same operand layouts / epilogues / split-K as gemm_tc.cuh (which remains for small problems).
+//
+// Epilogue: SIXTEEN warps per CTA (576 threads).  The fused epilogues are latency-bound per warp (TMEM load -> math ->
+// staging write -> TMA store; issue slots were ~50 % used with two epilogue warps per scheduler, and the K = 768 tiles
+// were EPILOGUE-bound: tensor pipe 47-58 %, profiles/r1_ncu_hot_v15.md), so the fix is thread-level parallelism, not
+// fewer instructions: warps work in PAIRS on one [32 rows x 64 cols] box -- each warp takes 32 of the 64 columns, in
+// two 16-column steps to stay under 112 registers -- and share the pair's staging / aux boxes (shared memory per CTA
+// is unchanged), synchronised by one named barrier per pair.
 #pragma once
 #include "gemm_tc.cuh"
 #include "epilogue_staged.cuh"
 
 namespace mtvaf {
+
+constexpr int kEpiWarps2 = 16;                       // epilogue warps per CTA of the pair kernel
+constexpr int kEpiPairs = kEpiWarps2 / 2;            // warp pairs = owners of the staging / aux boxes
+constexpr int kGemmThreads2 = 64 + kEpiWarps2 * 32;  // + TMA producer warp + MMA issuer warp
+
 namespace ptx {
+
+// named barrier `id` (1..15; 0 is __syncthreads) over `count` threads (a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  tmem_ld_32x32b_x16(taddr, r);
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -103,7 +123,7 @@ struct Gemm2Smem {
   static constexpr int kABytes = BM * BK * 2;          // 128 rows of A per CTA: 16 KB
   static constexpr int kBBytes = (BN / 2) * BK * 2;    // half of the B tile per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = kEpiWarps * StagedEpi<EPI>::kBytesPerWarp;   // staging + aux boxes
+  static constexpr int kEpiBytes = kEpiPairs * StagedEpi<EPI>::kBytesPerWarp;   // staging + aux boxes, one set per warp PAIR
   static constexpr int kBarrierBytes = 512;
   static constexpr int kAvail = 227 * 1024 - 1024 - kBarrierBytes - kEpiBytes;
 #ifndef MTVAF_GEMM_MAX_STAGES
@@ -116,7 +136,7 @@ struct Gemm2Smem {
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads2, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                      const __grid_constant__ CUtensorMap tmAux, const EpiArgs ep_in, int M, int N, int K, int splits,
@@ -135,8 +155,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tmem_full = empty_bar + S::kStages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint64_t* aux_bar = tmem_empty + 2;              // [kEpiWarps][2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2 * kEpiWarps);
+  uint64_t* aux_bar = tmem_empty + 2;              // [kEpiPairs][2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2 * kEpiPairs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,9 +179,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 2 * kEpiWarps);     // both CTAs' epilogue warps (used in the leader only)
+      mbar_init(&tmem_empty[s], 2 * kEpiWarps2);    // both CTAs' epilogue warps (used in the leader only)
     }
-    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < 2 * kEpiPairs; ++s) mbar_init(&aux_bar[s], 1);
     fence_barrier_init();
   }
   constexpr int kTmemCols = 2 * BN;
@@ -241,20 +261,24 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue warps (2..9), both CTAs =====================
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    // ===================== epilogue warps (2..17), both CTAs =====================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int sub = (warp - 2) >> 2;                 // 0..3: which quarter of the tile's columns
+    const int half = sub >> 1;                       // which half of the tile's columns the warp PAIR owns
+    const int part = sub & 1;                        // which 32 columns of each 64-column box this warp computes
+    const int pair = half * 4 + quad;                // 0..7: owner of one set of staging / aux boxes
+    const int bar_id = 1 + pair;                     // named barrier of the pair (64 threads)
     int acc = 0;
     uint32_t acc_phase = 0;
     if (SE::kStaged && ep.staged) {
       // ---- coalesced path: TMA-loaded aux boxes, smem-staged TMA stores (epilogue_staged.cuh)
-      constexpr int kBoxes = BN / 128;               // 64-column boxes per warp per tile
-      const int ew = warp - 2;
-      uint8_t* my = epi_smem + ew * SE::kBytesPerWarp;
+      constexpr int kBoxes = BN / 128;               // 64-column boxes per warp pair per tile
+      const bool issuer = part == 0 && lane == 0;    // the pair's TMA thread
+      uint8_t* my = epi_smem + pair * SE::kBytesPerWarp;
       uint8_t* out_box = my;                         // [kOutBufs] boxes
       uint8_t* aux_box = my + SE::kOutBufs * kEpiBoxBytes;   // [2] boxes
-      uint64_t* my_bar = aux_bar + 2 * ew;
-      // prefetch iterator over this warp's valid boxes (runs two boxes ahead of the consumer)
+      uint64_t* my_bar = aux_bar + 2 * pair;
+      // prefetch iterator over this pair's valid boxes (runs two boxes ahead of the consumer; issuer thread only)
       int pf_item = cluster_id, pf_j = -1;
       auto pf_next = [&](int& row0, int& col0) -> bool {
         while (true) {
@@ -267,7 +291,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       };
       uint32_t used = 0;                             // boxes consumed so far (aux buffer = used & 1)
-      if (SE::kAux && lane == 0) {
+      if (SE::kAux && issuer) {
         for (int i = 0; i < 2; ++i) {
           int r0, c0;
           if (!pf_next(r0, c0)) break;
@@ -285,53 +309,57 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll 1
         for (int j = 0; j < kBoxes; ++j) {
           const int col0 = w.tn * BN + half * (BN / 2) + j * 64;
-          if (col0 >= N) continue;                   // warp-uniform
+          if (col0 >= N) continue;                   // pair-uniform
+          const int c32 = col0 + part * 32;          // this warp's 32 columns
           const uint32_t ab = used & 1;
-          const bool full = col0 + 64 <= N;
           const uint32_t out_a = smem_u32(out_box), aux_a = smem_u32(aux_box) + ab * kEpiBoxBytes;
-          // software pipeline over the two 32-column halves of the box: the TMEM load of half 1 and the bias loads
-          // are in flight while half 0 is computed; the staging box is only claimed (previous TMA store done
-          // READING it) right before the first write, i.e. after a whole half of math
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(t_addr + j * 64, r0);
-          float bias0[32], bias1[32];
-          epi_load_bias32(ep, col0, N, full, bias0);
+          // two 16-column steps; the TMEM load and the bias of step 1 are in flight while step 0 is computed
+          uint32_t ra[16], rb[16];
+          tmem_ld_32x32b_x16(t_addr + j * 64 + part * 32, ra);
+          float bias_a[16], bias_b[16];
+          epi_load_bias16(ep, c32, N, c32 + 16 <= N, bias_a);
+          uint32_t keep = 0xFFFFFFFFu;
+          if (EPI == MTVAF_EPI_RESID && ep.drop_threshold)
+            keep = dropout_mask32(ep.seed, (unsigned long long)row * (unsigned long long)N + c32, ep.drop_threshold);
           if (SE::kAux) mbar_wait(&my_bar[ab], (used >> 1) & 1);
-          uint4 aux4[4];
+          uint4 aux2[2];
           if (SE::kAux) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) aux4[g] = ld_shared_v4(aux_a + box_piece_off(lane, g));
+            for (int g = 0; g < 2; ++g) aux2[g] = ld_shared_v4(aux_a + box_piece_off(lane, part * 4 + g));
           }
           tmem_ld_wait();
-          tmem_ld_32x32b_x32(t_addr + j * 64 + 32, r1);
-          epi_load_bias32(ep, col0 + 32, N, full, bias1);
-          uint32_t o[16], p[16];
-          epi_compute32<EPI>(ep, r0, bias0, aux4, row, col0, N, o, p);
-          if (lane == 0) tma_store_wait_read<0>();
+          tmem_ld_32x32b_x16(t_addr + j * 64 + part * 32 + 16, rb);
+          epi_load_bias16(ep, c32 + 16, N, c32 + 32 <= N, bias_b);
+          uint32_t o[8], p[8];
+          epi_compute_groups<EPI, 2>(ep, ra, bias_a, aux2, keep, o, p);
+          // the pair's staging box is free once the previous TMA store has finished READING it
+          if (issuer) tma_store_wait_read<0>();
           __syncwarp();
+          named_bar_sync(bar_id, 64);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = box_piece_off(lane, g);
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t off = box_piece_off(lane, part * 4 + g);
             st_shared_v4(out_a + off, o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
             if (EPI == MTVAF_EPI_GELU)
               st_shared_v4(out_a + kEpiBoxBytes + off, p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
           }
           if (SE::kAux) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) aux4[g] = ld_shared_v4(aux_a + box_piece_off(lane, 4 + g));
+            for (int g = 0; g < 2; ++g) aux2[g] = ld_shared_v4(aux_a + box_piece_off(lane, part * 4 + 2 + g));
           }
           tmem_ld_wait();
-          epi_compute32<EPI>(ep, r1, bias1, aux4, row, col0 + 32, N, o, p);
+          epi_compute_groups<EPI, 2>(ep, rb, bias_b, aux2, keep >> 16, o, p);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = box_piece_off(lane, 4 + g);
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t off = box_piece_off(lane, part * 4 + 2 + g);
             st_shared_v4(out_a + off, o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
             if (EPI == MTVAF_EPI_GELU)
               st_shared_v4(out_a + kEpiBoxBytes + off, p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
           }
           fence_proxy_async_smem();                  // staging writes (and aux reads) ordered before the TMA ops
           __syncwarp();
-          if (lane == 0) {
+          named_bar_sync(bar_id, 64);                // both halves of the box staged, both warps done with the aux box
+          if (issuer) {
             tma_store_2d(&tmOut, out_box, col0, row0);
             if (EPI == MTVAF_EPI_GELU && ep.out2) tma_store_2d(&tmOut2, out_box + kEpiBoxBytes, col0, row0);
             tma_store_commit();
@@ -344,30 +372,34 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
           if (ep.colsum) {                           // kernel-uniform
-            // column sums of the box just staged (the bf16 values as stored): lane = column pair, 32 conflict-free
-            // 4-byte reads down the rows.  Rows past M hold epi(0) of zero-filled operand rows: excluded.
+            // column sums of the box just staged (the bf16 values as stored).  This warp: column pairs
+            // [16 part, 16 part + 16); lanes 0-15 sum rows 0-15, lanes 16-31 rows 16-31, combined by one shuffle.
+            // Rows past M hold epi(0) of zero-filled operand rows: excluded.  (The next box's staging writes come
+            // after its first named barrier, i.e. after both warps' reads here.)
             const int rows_ok = min(32, M - row0);
-            float s0 = 0.f, s1 = 0.f;
-            const uint32_t colb = out_a + ((lane & 3) << 2);
-            const int piece = lane >> 2;
-            // all 32 loads in flight at once (the epilogue is latency-bound here), two partial sums per column
-            uint32_t v[32];
+            const int cp = (lane & 15) + 16 * part;  // column pair 0..31 of the box
+            const int rbase = (lane >> 4) * 16;
+            const uint32_t colb = out_a + ((cp & 3) << 2);
+            const int piece = cp >> 2;
+            uint32_t v[16];
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[rr]) : "r"(colb + rr * 128 + ((piece ^ (rr & 7)) << 4)));
-            float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-            for (int rr = 0; rr < 32; rr += 2) {
-              const float2 fa = unpack_bf16x2(rr < rows_ok ? v[rr] : 0u);
-              const float2 fb = unpack_bf16x2(rr + 1 < rows_ok ? v[rr + 1] : 0u);
-              s0 += fa.x; s1 += fa.y;
-              t0 += fb.x; t1 += fb.y;
+            for (int rr = 0; rr < 16; ++rr) {
+              const int r_ = rbase + rr;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[rr]) : "r"(colb + r_ * 128 + ((piece ^ (r_ & 7)) << 4)));
             }
-            s0 += t0;
-            s1 += t1;
-            const int cc = col0 + 2 * lane;
-            if (cc < N) atomicAdd(ep.colsum + cc, s0);
-            if (cc + 1 < N) atomicAdd(ep.colsum + cc + 1, s1);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const float2 f = unpack_bf16x2(rbase + rr < rows_ok ? v[rr] : 0u);
+              s0 += f.x; s1 += f.y;
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            const int cc = col0 + 2 * cp;
+            if (lane < 16) {
+              if (cc < N) atomicAdd(ep.colsum + cc, s0);
+              if (cc + 1 < N) atomicAdd(ep.colsum + cc + 1, s1);
+            }
           }
           ++used;
         }
@@ -376,20 +408,20 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (lane == 0) tma_store_wait<0>();            // all output bytes written before the CTA retires
+      if (issuer) tma_store_wait<0>();               // all output bytes written before the CTA retires
       __syncwarp();
     } else {
-      // ---- direct path (fp32 outputs, atomics, row reductions, unaligned outputs)
-      constexpr int kChunks = BN / 64;
+      // ---- direct path (fp32 outputs, atomics, row reductions, unaligned outputs): a quarter of the columns per warp
+      constexpr int kChunks = BN / 128;
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const WorkItem w = decode_item(item, n_tiles_n, n_tiles_m, kb_total, kb_per);
-        const int n0 = w.tn * BN + half * (BN / 2);
+        const int n0 = w.tn * BN + sub * (BN / 4);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const int row = 2 * w.m0 + rank * BM + quad * 32 + lane;
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + sub * (BN / 4);
         float rowacc = 0.f;
-#pragma unroll 2
+#pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_addr + c * 32, r);
@@ -464,7 +496,7 @@ int launch_gemm_tc2(const void* A, int64_t lda, const void* B, int64_t ldb, int 
     MTVAF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  kern<<<2 * clusters, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, epl, M, N, K, splits, kb_per);
+  kern<<<2 * clusters, kGemmThreads2, S::kTotal, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, epl, M, N, K, splits, kb_per);
   MTVAF_LAUNCH_CHECK();
   return 0;
 }

@@ -5,6 +5,7 @@
 //   * TwoWordPSDProbe pairwise squared distances  (probes/probe.py:25-46)
 //   * linear-chain CRF NLL (+grad) and Viterbi    (pytorch-crf semantics; bert_model.py:511,521)
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/mtvaf_b200.h"
 
 namespace mtvaf {
@@ -62,51 +63,86 @@ gate_fwd_kernel(const T* __restrict__ guids, const float* __restrict__ logits, i
 // columns' four split values and their gradient accumulators in registers across ALL layers, so the prompt
 // (guids) is read once, d_guids is written once (plain store) and d_kv is streamed exactly once; the per-layer
 // gate gradients are reduced warp-wise into shared memory and leave the block as one atomic per (layer, split).
+//
+// d_kv (600 MB at B=512, the kernel's whole cost) is STAGED through shared memory by 1-D bulk copies
+// (cp.async.bulk): per layer the block's data are two contiguous runs of `hid` floats (the K and the V slot of its
+// prefix row); a group of GL layers is requested at once on one mbarrier, two groups in flight.  With plain loads
+// (6 scalar loads per thread and layer, no memory-level parallelism to speak of) the kernel sat at 1.2 TB/s.
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_bwd_kernel(const float* __restrict__ d_kv, const T* __restrict__ guids, const float* __restrict__ gates,
-                int n_layers, int n_img, int B, int hid, float* __restrict__ d_guids, float* __restrict__ d_gates) {
-  extern __shared__ float part[];                     // [8 warps][n_layers * 4]
+                int n_layers, int n_img, int B, int hid, int GL, float* __restrict__ d_guids,
+                float* __restrict__ d_gates) {
+  extern __shared__ __align__(128) uint8_t gsm[];
   constexpr int KMAX = 8;                             // columns per thread: 2*hid <= 2048
   const int rowr = blockIdx.x;
   const int row = rowr >> 2, r = rowr & 3;
   const int j = row / B, b = row - j * B;
   const int S2 = 2 * hid, W = 4 * S2, P = 4 * n_img;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = reinterpret_cast<float*>(gsm);                               // [2][GL][2 * hid]
+  float* part = stage + 2 * GL * S2;                                          // [8 warps][n_layers * 4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 8 * n_layers * 4);      // one per buffer
   const T* src = guids + ((long long)row * 4 + r) * W;
   float* dsrc = d_guids + ((long long)row * 4 + r) * W;
   const long long kv_stride_l = 2LL * B * P * hid;
+  const int n_groups = (n_layers + GL - 1) / GL;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int g) {                            // one thread: layers [g*GL, ...) into buffer g & 1
+    const int l0 = g * GL, nl = min(GL, n_layers - l0);
+    float* dst = stage + (g & 1) * GL * S2;
+    ptx::mbar_arrive_expect_tx(&bars[g & 1], (uint32_t)(nl * S2 * sizeof(float)));
+    for (int l = 0; l < nl; ++l)
+      for (int slot = 0; slot < 2; ++slot)
+        ptx::bulk_load_1d(dst + l * S2 + slot * hid,
+                          d_kv + (l0 + l) * kv_stride_l + ((long long)slot * B + b) * P * hid + (long long)(j * 4 + r) * hid,
+                          (uint32_t)(hid * sizeof(float)), &bars[g & 1]);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (n_groups > 1) issue(1);
+  }
   float x[KMAX][4], acc[KMAX][4];
-  long long off[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int c = threadIdx.x + k * 256;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { x[k][i] = c < S2 ? to_f<T>(src[i * S2 + c]) : 0.f; acc[k][i] = 0.f; }
-    const int slot = c / hid, cc = c - slot * hid;
-    off[k] = ((long long)slot * B + b) * P * hid + (long long)(j * 4 + r) * hid + cc;
   }
   const float* grow = gates + (long long)row * n_layers * 4;
-  // the kernel is bound by bytes in flight (6 scalar loads per thread and layer left HBM at 1.2 TB/s): unrolled by
-  // four layers the loads of the next layers are issued above this layer's shuffles
-#pragma unroll 4
-  for (int l = 0; l < n_layers; ++l) {
-    const float g0 = grow[l * 4 + 0], g1 = grow[l * 4 + 1], g2 = grow[l * 4 + 2], g3 = grow[l * 4 + 3];
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-    const float* dl = d_kv + l * kv_stride_l;
+  for (int g = 0; g < n_groups; ++g) {
+    const int l0 = g * GL, nl = min(GL, n_layers - l0);
+    const float* buf = stage + (g & 1) * GL * S2;
+    ptx::mbar_wait(&bars[g & 1], (g >> 1) & 1);
+    for (int ll = 0; ll < nl; ++ll) {
+      const int l = l0 + ll;
+      const float g0 = grow[l * 4 + 0], g1 = grow[l * 4 + 1], g2 = grow[l * 4 + 2], g3 = grow[l * 4 + 3];
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+      const float* dl = buf + ll * S2;                 // column c = slot * hid + cc: exactly the staged order
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int c = threadIdx.x + k * 256;
-      if (c < S2) {
-        const float d = dl[off[k]];
-        p0 += d * x[k][0]; p1 += d * x[k][1]; p2 += d * x[k][2]; p3 += d * x[k][3];
-        acc[k][0] += g0 * d; acc[k][1] += g1 * d; acc[k][2] += g2 * d; acc[k][3] += g3 * d;
+      for (int k = 0; k < KMAX; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c < S2) {
+          const float d = dl[c];
+          p0 += d * x[k][0]; p1 += d * x[k][1]; p2 += d * x[k][2]; p3 += d * x[k][3];
+          acc[k][0] += g0 * d; acc[k][1] += g1 * d; acc[k][2] += g2 * d; acc[k][3] += g3 * d;
+        }
+      }
+      p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2); p3 = warp_sum(p3);
+      if (lane == 0) {
+        float* pp = part + warp * n_layers * 4 + l * 4;
+        pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
       }
     }
-    p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2); p3 = warp_sum(p3);
-    if (lane == 0) {
-      float* pp = part + warp * n_layers * 4 + l * 4;
-      pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
+    if (g + 2 < n_groups) {                            // this buffer is free again: request the group after next
+      ptx::fence_proxy_async_smem();                   // generic-proxy reads before the async-proxy overwrite
+      __syncthreads();
+      if (threadIdx.x == 0) issue(g + 2);
     }
   }
 #pragma unroll
@@ -455,15 +491,29 @@ extern "C" int mtvaf_gate_bwd(const float* d_kv, const void* guids, const float*
   MTVAF_REQUIRE(d_kv && guids && gate_logits && gates && d_guids && d_gates_scratch && d_gate_logits,
                 "gate_bwd: null argument");
   MTVAF_REQUIRE(n_layers > 0 && n_img > 0 && B > 0 && hid > 0 && 2 * hid <= 2048, "gate_bwd: bad shape (hid <= 1024)");
+  MTVAF_REQUIRE(hid % 4 == 0 && (reinterpret_cast<uintptr_t>(d_kv) & 15) == 0,
+                "gate_bwd: d_kv must be 16-byte aligned with hid %% 4 == 0 (bulk copies)");
   const int blocks = n_img * B * 4;
-  const size_t sm = (size_t)8 * n_layers * 4 * sizeof(float);
+  // layers per staged group: two groups (double buffer) of GL layers x 2 slots x hid floats, ~36 KB per group so that
+  // three blocks share an SM
+  int GL = (36 * 1024) / (2 * hid * (int)sizeof(float));
+  if (GL < 1) GL = 1;
+  if (GL > n_layers) GL = n_layers;
+  const size_t sm = (size_t)2 * GL * 2 * hid * sizeof(float) + (size_t)8 * n_layers * 4 * sizeof(float) + 16;
   cudaStream_t st = (cudaStream_t)stream;
+  static bool set = false;
+  if (!set) {
+    MTVAF_CHECK_CUDA(cudaFuncSetAttribute(gate_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MTVAF_CHECK_CUDA(cudaFuncSetAttribute(gate_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    set = true;
+  }
+  MTVAF_REQUIRE(sm <= 100 * 1024, "gate_bwd: shared memory");
   if (dtype == MTVAF_BF16)
     gate_bwd_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>(d_kv, (const __nv_bfloat16*)guids, gates, n_layers, n_img,
-                                                            B, hid, d_guids, d_gates_scratch);
+                                                            B, hid, GL, d_guids, d_gates_scratch);
   else
-    gate_bwd_kernel<float><<<blocks, 256, sm, st>>>(d_kv, (const float*)guids, gates, n_layers, n_img, B, hid, d_guids,
-                                                    d_gates_scratch);
+    gate_bwd_kernel<float><<<blocks, 256, sm, st>>>(d_kv, (const float*)guids, gates, n_layers, n_img, B, hid, GL,
+                                                    d_guids, d_gates_scratch);
   MTVAF_LAUNCH_CHECK();
   const long long groups = (long long)n_img * B * n_layers;
   gate_logit_bwd_kernel<<<(int)((groups + 255) / 256), 256, 0, st>>>(d_gates_scratch, gates, gate_logits, groups,
