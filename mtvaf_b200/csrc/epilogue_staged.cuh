@@ -1,7 +1,7 @@
 // Coalesced GEMM epilogue for the CTA-pair tcgen05 kernel: every epilogue warp owns a [32 rows x 64 cols]
 // bf16 box of the output tile at a time.  The residual / pre-activation operand of the fused epilogues
 // (models/modeling_roberta.py:297-298,366 and their backward) arrives by TMA into a per-warp
-// SWIZZLE_128B box (double buffered, prefetched two boxes ahead), the results are written to a per-warp
+// SWIZZLE_128B box (prefetched one box ahead; shared memory goes to the operand ring first), the results are written to a per-warp
 // staging box in shared memory (conflict-free 16-byte pieces) and leave with ONE TMA store per box, so
 // global traffic is full 128-byte lines instead of 32 scattered 16-byte pieces per warp instruction.
 #pragma once
@@ -19,7 +19,13 @@ struct StagedEpi {
                                    MODE == MTVAF_EPI_MUL_DTANH);
   static constexpr bool kAux = (MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU || MODE == MTVAF_EPI_MUL_DTANH);
   static constexpr int kOutBufs = kStaged ? ((MODE == MTVAF_EPI_GELU) ? 2 : 1) : 0;
-  static constexpr int kAuxBufs = kAux ? 2 : 0;
+#ifndef MTVAF_EPI_AUX_BUFS
+// aux boxes per warp pair: 1 = the next box's operand is requested as soon as both warps have read the current one
+// (the operand ring gets the 32 KB back: 5 stages instead of 4 for RESID / xGELU' / xtanh'), 2 = prefetched two boxes
+// ahead.  Measured in isolation at M = 65536 (tools/bench_gemm.py, round 2): 1 is 5-14 % faster on every fused-aux variant.
+#define MTVAF_EPI_AUX_BUFS 1
+#endif
+  static constexpr int kAuxBufs = kAux ? MTVAF_EPI_AUX_BUFS : 0;
   static constexpr int kBytesPerWarp = (kOutBufs + kAuxBufs) * kEpiBoxBytes;
 };
 

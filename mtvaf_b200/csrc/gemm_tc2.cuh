@@ -276,7 +276,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool issuer = part == 0 && lane == 0;    // the pair's TMA thread
       uint8_t* my = epi_smem + pair * SE::kBytesPerWarp;
       uint8_t* out_box = my;                         // [kOutBufs] boxes
-      uint8_t* aux_box = my + SE::kOutBufs * kEpiBoxBytes;   // [2] boxes
+      uint8_t* aux_box = my + SE::kOutBufs * kEpiBoxBytes;   // [kAuxBufs] boxes
+      constexpr int kAB = SE::kAuxBufs > 0 ? SE::kAuxBufs : 1;
       uint64_t* my_bar = aux_bar + 2 * pair;
       // prefetch iterator over this pair's valid boxes (runs two boxes ahead of the consumer; issuer thread only)
       int pf_item = cluster_id, pf_j = -1;
@@ -292,7 +293,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       };
       uint32_t used = 0;                             // boxes consumed so far (aux buffer = used & 1)
       if (SE::kAux && issuer) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kAB; ++i) {
           int r0, c0;
           if (!pf_next(r0, c0)) break;
           mbar_arrive_expect_tx(&my_bar[i], kEpiBoxBytes);
@@ -311,7 +312,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int col0 = w.tn * BN + half * (BN / 2) + j * 64;
           if (col0 >= N) continue;                   // pair-uniform
           const int c32 = col0 + part * 32;          // this warp's 32 columns
-          const uint32_t ab = used & 1;
+          const uint32_t ab = kAB == 2 ? (used & 1) : 0;
+          const uint32_t ab_phase = kAB == 2 ? ((used >> 1) & 1) : (used & 1);
           const uint32_t out_a = smem_u32(out_box), aux_a = smem_u32(aux_box) + ab * kEpiBoxBytes;
           // two 16-column steps; the TMEM load and the bias of step 1 are in flight while step 0 is computed
           uint32_t ra[16], rb[16];
@@ -321,7 +323,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint32_t keep = 0xFFFFFFFFu;
           if (EPI == MTVAF_EPI_RESID && ep.drop_threshold)
             keep = dropout_mask32(ep.seed, (unsigned long long)row * (unsigned long long)N + c32, ep.drop_threshold);
-          if (SE::kAux) mbar_wait(&my_bar[ab], (used >> 1) & 1);
+          if (SE::kAux) mbar_wait(&my_bar[ab], ab_phase);
           uint4 aux2[2];
           if (SE::kAux) {
 #pragma unroll

@@ -46,6 +46,9 @@ def main():
             t["fwd_resid_drop"] = timeit(lambda: ops.linear_fwd(x, w, bias, out=out, mode=Lb.EPI_RESID, aux=res_in,
                                                                  p_drop=0.1, seed=5))
             t["dgrad"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx))
+            pre = torch.randn(M, K, device="cuda").bfloat16()
+            t["dgrad_dgelu"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx, mode=Lb.EPI_MUL_DGELU, aux=pre))
+            t["dgrad_resid"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx, mode=Lb.EPI_RESID, aux=pre))
             t["wgrad"] = timeit(lambda: ops.linear_wgrad(dy, x, dw))
             for k, v in t.items():
                 r["%s_%s_tflops" % (impl, k)] = round(fl / v / 1e9, 1)
