@@ -21,7 +21,7 @@
 namespace mtvaf {
 using namespace ptx;
 
-constexpr int kFwdThreads = 256;
+constexpr int kFwdThreadsSmall = 256, kFwdThreadsBig = 512;   // 2 / 4 threads per query row
 constexpr float kFwdLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -30,11 +30,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// BIG (N16 > 192: one CTA per SM) runs 16 warps = four threads per query row (+9 % at L = 512, +8 % at P = 100, measured
+// round 2); the small shapes (two CTAs per SM) are faster with 8 warps = two threads per row.
 template <bool BIG>
-__global__ void __launch_bounds__(kFwdThreads, BIG ? 1 : 2)
+__global__ void __launch_bounds__(BIG ? kFwdThreadsBig : kFwdThreadsSmall, BIG ? 1 : 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmKp, const __grid_constant__ CUtensorMap tmVp,
                    AttnTcArgs a, __nv_bfloat16* __restrict__ ctx, long long ld_ctx, float* __restrict__ lse_out) {
+  constexpr int kFwdThreads = BIG ? kFwdThreadsBig : kFwdThreadsSmall;
+  constexpr int NPART = kFwdThreads / 128;           // threads per query row
   constexpr int S_COLS = BIG ? 448 : 192;            // TMEM columns reserved for S; O follows
   constexpr int TMEM_COLS = BIG ? 512 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -46,12 +50,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = sK + key_rows * 128;
   uint8_t* sP = sV + key_rows * 128;                 // n_chunks x [128][64] bf16
   float* sMask = reinterpret_cast<float*>(sP + n_chunks * 16384);     // [N16], additive mask * log2(e)
-  float* sExch = sMask + ((a.N16 + 15) / 16) * 16;   // [2][2][128]: partial row max / row sum per column half
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 512);          // Q+K landed, s, o, V landed
+  float* sExch = sMask + ((a.N16 + 15) / 16) * 16;   // [2][4][128]: partial row max / row sum per part of the units
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 1024);         // Q+K landed, s, o, V landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;       // TMEM lane group / which half of the units
+  const int quad = warp & 3, half = warp >> 2;       // TMEM lane group / which part of the units (0..NPART-1)
   const int row = quad * 32 + lane;
   const int H = a.nh * 64;
   const int q_tiles = (a.L + 127) / 128;
@@ -97,14 +101,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
   const int units = a.N16 >> 3;
 
-  // key `k` of batch row `b` -> additive mask; keys >= N16 are never read (N16 <= 448 < 2 * kFwdThreads)
+  // key `k` of batch row `b` -> additive mask; keys >= N16 are never read (N16 <= 448 < kFwdThreads)
   auto fetch_mask = [&](int b, int k) -> float {
     if (k >= a.N16) return 0.f;
     if (k < a.P8) return (k < a.P) ? 0.f : -INFINITY;
     const int t = k - a.P8;
     return (t < a.Lk) ? (a.key_mask[(long long)b * a.L + a.kt0 + t] != 0 ? 0.f : -10000.0f * kFwdLog2e) : -INFINITY;
   };
-  float mask_next[2] = {0.f, 0.f};
+  float mask_next[2] = {0.f, 0.f};                   // (N16 <= 448 < 2 * kFwdThreads)
   if ((int)blockIdx.x < n_items) {
     const int b0 = (int)blockIdx.x / q_tiles / a.nh;
     mask_next[0] = fetch_mask(b0, tid);
@@ -149,7 +153,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // ---- pass 1: row max of (S / sqrt(d) + mask) * log2 e over this thread's units
     float mx = -INFINITY;
-    for (int u = half; u < units; u += 2) {
+    for (int u = half; u < units; u += NPART) {
       const int c = u << 3;
       uint32_t r[8];
       tmem_ld_32x32b_x8(t_row + c, r);
@@ -163,7 +167,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     sExch[half * 128 + row] = mx;
     __syncthreads();
-    const float mx2 = fmaxf(sExch[row], sExch[128 + row]);   // finite: key 0 exists and S is finite
+    // finite: key 0 exists and S is finite (a part without units contributes -inf)
+    float mx2 = fmaxf(sExch[row], sExch[128 + row]);
+    if (NPART == 4) mx2 = fmaxf(mx2, fmaxf(sExch[256 + row], sExch[384 + row]));
 
     // ---- pass 2: P = exp2(x - max), row sum, dropout, bf16 P -> shared memory.  With dropout the 1/(1-p) scale
     // rides in the exponent (max - log2(scale)): P is born scaled, the row sum is corrected once at the end.
@@ -171,7 +177,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
     const float mxs = a.drop_thr ? mx2 - log2f(a.drop_scale) : mx2;
     float sum = 0.f;
-    for (int u = half; u < units; u += 2) {
+    for (int u = half; u < units; u += NPART) {
       const int c = u << 3;
       uint32_t r[8];
       tmem_ld_32x32b_x8(t_row + c, r);
@@ -191,7 +197,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
       *reinterpret_cast<uint4*>(sP + (u >> 3) * 16384 + prow_off + (((u & 7) ^ row8) << 4)) = w;
     }
-    sExch[256 + half * 128 + row] = sum;
+    sExch[512 + half * 128 + row] = sum;
     fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -210,7 +216,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(&bars[2]);
     }
     __syncwarp();
-    const float total = sExch[256 + row] + sExch[384 + row];
+    float total = sExch[512 + row] + sExch[640 + row];
+    if (NPART == 4) total += sExch[768 + row] + sExch[896 + row];
     mbar_wait(&bars[2], ph);
     __syncwarp();
     tc_fence_after();
@@ -223,7 +230,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // O = (sum_k keep_k P'_k V_k) / (sum_k P'_k / scale) with P' = scale * P
     const float inv = a.drop_scale / total;
     const bool valid = q < a.L;
-    {
+    if constexpr (NPART == 4) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + S_COLS + half * 16, r);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* o = reinterpret_cast<uint4*>(ctx + ((long long)b * a.L + q) * ld_ctx + h * 64 + half * 16);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) * inv, __uint_as_float(r[v * 8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]) * inv, __uint_as_float(r[v * 8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]) * inv, __uint_as_float(r[v * 8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]) * inv, __uint_as_float(r[v * 8 + 7]) * inv);
+          o[v] = w;
+        }
+      }
+    } else {
       uint32_t r[32];
       tmem_ld_32x32b_x32(t_row + S_COLS + half * 32, r);
       tmem_ld_wait();
@@ -256,7 +279,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 size_t attn_fwd_tc_smem(const AttnTcArgs& a) {
   const int key_rows = a.P8 + a.L64;
   const int n_chunks = (a.N16 + 63) / 64;
-  return 1024 + 16384 + 2 * (size_t)key_rows * 128 + (size_t)n_chunks * 16384 + ((a.N16 + 15) / 16) * 64 + 2048 + 64;
+  return 1024 + 16384 + 2 * (size_t)key_rows * 128 + (size_t)n_chunks * 16384 + ((a.N16 + 15) / 16) * 64 + 4096 + 64;
 }
 
 int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int64_t ld_ctx, float* lse,
@@ -272,14 +295,14 @@ int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int6
     }
     const int per_sm = 2 * smem <= 227 * 1024 ? 2 : 1;
     const int grid = n_items < per_sm * sm_count() ? n_items : per_sm * sm_count();
-    attn_fwd_tc_kernel<false><<<grid, kFwdThreads, smem, st>>>(m.q, m.kv, m.kp, m.vp, a, (__nv_bfloat16*)ctx, ld_ctx, lse);
+    attn_fwd_tc_kernel<false><<<grid, kFwdThreadsSmall, smem, st>>>(m.q, m.kv, m.kp, m.vp, a, (__nv_bfloat16*)ctx, ld_ctx, lse);
   } else {
     if (!set1) {
       MTVAF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       set1 = true;
     }
     const int grid = n_items < sm_count() ? n_items : sm_count();
-    attn_fwd_tc_kernel<true><<<grid, kFwdThreads, smem, st>>>(m.q, m.kv, m.kp, m.vp, a, (__nv_bfloat16*)ctx, ld_ctx, lse);
+    attn_fwd_tc_kernel<true><<<grid, kFwdThreadsBig, smem, st>>>(m.q, m.kv, m.kp, m.vp, a, (__nv_bfloat16*)ctx, ld_ctx, lse);
   }
   MTVAF_LAUNCH_CHECK();
   return 0;

@@ -30,14 +30,6 @@ constexpr int kGemmThreads2 = 64 + kEpiWarps2 * 32;  // + TMA producer warp + MM
 
 namespace ptx {
 
-// named barrier `id` (1..15; 0 is __syncthreads) over `count` threads (a multiple of 32)
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  tmem_ld_32x32b_x16(taddr, r);
-}
-
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

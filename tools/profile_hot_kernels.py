@@ -1,4 +1,4 @@
-"""Runs every hot kernel variant of the training step at the bench shape (B=256, L=128, P=16, bf16) twice, so one
+"""Runs every hot kernel variant of the training step at the bench shape (B=256 or env B=512, L=128, P=16, bf16) twice, so one
 
   ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:'gemm_bf16_tc2|attn_|layernorm_bwd' -o gpurun_out/hot python tools/profile_hot_kernels.py
@@ -13,7 +13,7 @@ from mtvaf_b200 import ops, lib as Lb
 
 
 def main():
-    B, Lq, P, nh, d = 256, 128, 16, 12, 64
+    B, Lq, P, nh, d = int(os.environ.get("B", 256)), 128, 16, 12, 64      # B=512 = the bench batch
     H = nh * d
     T = B * Lq
     dev = "cuda"
