@@ -223,6 +223,7 @@ class Engine:
         self.base_seed = ((torch.initial_seed() ^ 0x5EED) + 7919 * rank) & 0x7FFFFFFF
         self._kv_internal_ptr = None       # prefix tensor handed from the fusion stack to the encoder within one forward
         self._dkv32: Dict[int, torch.Tensor] = {}
+        self.pre_backward_hook: Optional[Callable[[], None]] = None    # DP: called before a backward touches the flat G
         self.layer_grad_hook: Optional[Callable[[int], None]] = None   # DP: called when layer i's grads are final
         self.tail_grad_hook: Optional[Callable[[], None]] = None       # DP: called when the embedding grads are final
 
@@ -325,6 +326,8 @@ class Engine:
         c, f, e = self.cfg, self.flat, self.enc_prefix
         B, Lq, H, nh, d = saved["B"], saved["L"], c.H, c.nh, c.d
         cd = self.compute_dtype
+        if self.pre_backward_hook:
+            self.pre_backward_hook()
         kv, mask = saved["kv"], saved["mask"]
         p_h, p_a = saved["p_h"], saved["p_a"]
         step = saved["step"]
@@ -590,6 +593,8 @@ class Engine:
         c, f = self.cfg, self.flat
         B, Lq, H = saved["B"], saved["L"], c.H
         T = B * Lq
+        if self.pre_backward_hook:
+            self.pre_backward_hook()
         grads = {}
         d_em = saved["d_em"]
         n_tags = d_em.shape[-1]
@@ -707,6 +712,8 @@ def _span_heads_bwd(self, saved, dloss: torch.Tensor):
     B, Lq, H = saved["B"], saved["L"], c.H
     T = B * Lq
     cd = self.compute_dtype
+    if self.pre_backward_hook:
+        self.pre_backward_hook()
     grads = {}
     d_ae, d_ac = saved["d_ae"], saved["d_ac"]
     ops.scale_by_device_scalar(d_ae, dloss)

@@ -53,6 +53,16 @@ class FlatAdamW:
             else:
                 cur = [o, o + k, hit[0], hit[1]]
                 self.ranges.append(cur)
+        # a range must lie entirely inside or outside the bf16-shadowed prefix [0, cast_end) of the flat buffer: the
+        # fused kernel refreshes the shadow of the ranges it updates, and a straddling range would silently keep a stale
+        # shadow for its first part (latent with today's parameter order)
+        split = []
+        for a, b, lr_, wd_ in self.ranges:
+            if a < f.cast_end < b:
+                split += [[a, f.cast_end, lr_, wd_], [f.cast_end, b, lr_, wd_]]
+            else:
+                split.append([a, b, lr_, wd_])
+        self.ranges = split
         self.m = torch.zeros(f.total, dtype=F32, device=f.device)
         self.v = torch.zeros(f.total, dtype=F32, device=f.device)
         self.t = 0
@@ -172,9 +182,42 @@ class GradSync:
         emb = [n for n in getattr(flat, "names", []) if ".embeddings." in n or n.startswith("embeddings.")]
         if emb and max(flat.offsets[n][0] + flat.offsets[n][1] for n in emb) + 64 >= flat.total:
             self._emb_lo = min(flat.offsets[n][0] for n in emb)
+        self._enabled = True
         if self.world > 1:
             engine.layer_grad_hook = self._on_layer
             engine.tail_grad_hook = self._on_embeddings
+            engine.pre_backward_hook = self._before_backward
+
+    # ------------------------------------------------------------------ gradient accumulation
+    def no_sync(self):
+        """Context manager for the micro-batches of a gradient-accumulation window that do NOT end in an optimizer
+        step (the reference trainer's `gradient_accumulation_steps`, modules/train.py:620): their backward passes only
+        accumulate into the flat gradient buffer; the backward of the LAST micro-batch (outside this context) reduces
+        the sums.  (Reducing every micro-batch is also correct -- an average of averages -- it only costs bandwidth.)"""
+        sync = self
+
+        class _Ctx:
+            def __enter__(self_):
+                sync._enabled = False
+
+            def __exit__(self_, *exc):
+                sync._enabled = True
+                return False
+        return _Ctx()
+
+    def _before_backward(self):
+        """A backward that starts while all-reduces of a previous backward are still in flight (two backward passes
+        without an optimizer step between them) would accumulate into slices NCCL is still reading / writing on the
+        side stream: make this stream wait for them first."""
+        if self.works or self.tail_works:
+            for w in self.works:
+                w.wait()
+            for w in self.tail_works:
+                w.wait()
+            self.works.clear()
+            self.tail_works.clear()
+            self.done_layers.clear()
+            self._emb_done = False
 
     # ------------------------------------------------------------------ ranges
     def _clip(self, lo: int, hi: int):
@@ -203,7 +246,7 @@ class GradSync:
     def _on_embeddings(self):
         """Called by Engine.encoder_bwd right after the embedding backward: the embedding tables are 80 % of the
         tail, and the fusion backward that still follows hides their all-reduce."""
-        if self._emb_lo is None or self._emb_done:
+        if self._emb_lo is None or self._emb_done or not self._enabled:
             return
         for a, b in self._clip(self._emb_lo, self.engine.flat.total):
             self._reduce(self.engine.flat.G[a:b], tail=True)
@@ -228,6 +271,8 @@ class GradSync:
         (self.tail_works if tail else self.works).append(w)
 
     def _on_layer(self, i: int):
+        if not self._enabled:
+            return
         a, b = self.engine.flat.layer_ranges[i]
         self.done_layers.add(i)
         for a2, b2 in self._clip(a, b):

@@ -185,6 +185,64 @@ def test_gradsync_world2_gloo(fired):
     assert all(r[1] == "ok" for r in res), res
 
 
+def _worker_accum(rank, world, port, q):
+    """Gradient accumulation (the reference trainer's gradient_accumulation_steps): micro-batch 1 under no_sync() only
+    accumulates, micro-batch 2 reduces the SUM; and two backward passes WITHOUT no_sync (average of averages) give the
+    same result, the pre-backward hook waiting for the first pass's all-reduces before the second one accumulates."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mtvaf_b200.optim import GradSync
+        layer_ranges = [(0, 512), (512, 1024)]
+        total = 2048
+        g1 = lambda r: torch.randn(total, generator=torch.Generator().manual_seed(10 + r))
+        g2 = lambda r: torch.randn(total, generator=torch.Generator().manual_seed(20 + r))
+        expect = sum(g1(r) + g2(r) for r in range(world)) / world
+        for use_no_sync in (True, False):
+            eng = _fake_engine(total, layer_ranges, rank)
+            eng.pre_backward_hook = None
+            sync = GradSync(eng)
+            assert eng.pre_backward_hook is not None
+            eng.flat.G.copy_(g1(rank))                            # "backward" of micro-batch 1
+            if use_no_sync:
+                with sync.no_sync():
+                    eng.pre_backward_hook()
+                    for i in (1, 0):
+                        eng.layer_grad_hook(i)
+                    eng.tail_grad_hook()
+                assert not sync.works and not sync.done_layers   # nothing was reduced
+            else:
+                eng.pre_backward_hook()
+                for i in (1, 0):
+                    eng.layer_grad_hook(i)
+            eng.pre_backward_hook()                              # micro-batch 2 starts: outstanding work is awaited
+            eng.flat.G.add_(g2(rank))                            # its wgrads accumulate on top
+            for i in (1, 0):
+                eng.layer_grad_hook(i)
+            sync.finish()
+            assert torch.allclose(eng.flat.G, expect, atol=1e-5), use_no_sync
+        q.put((rank, "ok"))
+    except Exception as e:                                       # pragma: no cover
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradsync_gradient_accumulation_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_accum, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_adamw_ranges_follow_reference_groups():
     """modules/train.py:894-926: 'bert' and 'encoder_conv' at args.lr, 'crf'/'fc' at 5e-2, everything else
     (projectors, ANP heads, probe) never updated."""
