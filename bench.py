@@ -309,14 +309,14 @@ def name_gemm(w, B, key):
     rows4, rows = 16 * B, 4 * B
     role = None
     if (a_mn, b_mn) == (0, 0):
-        role = {(T, 3 * H, H): "qkv_fwd", (T, H, H): "attn_out_fwd_resid", (T, I, H): "ffn1_fwd_gelu",
+        role = {(T, 3 * H, H): "qkv_fwd", (T, H, H): "attn_out_fwd_resid", (T, I, H): "ffn1_fwd_gelu(+grad)",
                 (T, H, I): "ffn2_fwd_resid", (rows4, 800, 3840): "fusion_mlp1_fwd_tanh",
                 (rows4, 8 * H, 800): "fusion_mlp2_fwd", (B, 2089, 8 * H): "anp_head_fwd",
                 (rows, 4 * w["layers"], 8 * H): "fusion_gate_logits_fwd", (T, 11, H): "tag_head_fwd",
                 (T, H, H // 2): "probe_dgrad"}.get((M, N, K))
     elif (a_mn, b_mn) == (0, 1):
         role = {(T, H, 3 * H): "qkv_dgrad_resid", (T, H, H): "attn_out_dgrad", (T, H, I): "ffn1_dgrad_resid",
-                (T, I, H): "ffn2_dgrad_dgelu_colsum", (T, H // 2, H): "probe_fwd",
+                (T, I, H): "ffn2_dgrad_mulgelugrad_colsum", (T, H // 2, H): "probe_fwd",
                 (rows4, 800, 8 * H): "fusion_mlp2_dgrad_dtanh", (B, 8 * H, 2089): "anp_head_dgrad",
                 (T, H, 11): "tag_head_dgrad"}.get((M, N, K))
     elif (a_mn, b_mn) == (1, 1):

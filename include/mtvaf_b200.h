@@ -25,7 +25,8 @@ extern "C" {
 
 #define MTVAF_ABI_VERSION 3   /* 2: MtvafEpilogue.colsum, mtvaf_attention_bwd_ex, mtvaf_set_sm_reserve
                                * 3: mtvaf_set_pairwise_impl, mtvaf_pack_features (tcgen05 TwoWord probe; feature wire format),
-                               *    mtvaf_attention_fwd_ws / _workspace_bytes (long-text tcgen05 attention), mtvaf_row_sqnorm */
+                               *    mtvaf_attention_fwd_ws / _workspace_bytes (long-text tcgen05 attention), mtvaf_row_sqnorm,
+                               *    MTVAF_EPI_GELU_GRAD / MTVAF_EPI_MUL_AUX */
 #define MTVAF_F32 0
 #define MTVAF_BF16 1
 
@@ -55,7 +56,10 @@ enum {
   MTVAF_EPI_MUL_DGELU = 5,  /* out = acc * gelu_erf'(aux)                  (backward of :365-366)  */
   MTVAF_EPI_MUL_DTANH = 6,  /* out = acc * (1 - aux^2)                                             */
   MTVAF_EPI_SQNORM = 7,     /* rowsum[m] += sum_n acc^2 ; out (optional) = acc   (probes/probe.py:74-78) */
-  MTVAF_EPI_ROWSCALE = 8    /* out = acc * rowscale[m]  (probe backward: 2 g_m T_m)                */
+  MTVAF_EPI_ROWSCALE = 8,   /* out = acc * rowscale[m]  (probe backward: 2 g_m T_m)                */
+  MTVAF_EPI_GELU_GRAD = 9,  /* out = gelu(acc+bias); out2 (required) = gelu'(acc+bias): the derivative is computed in the
+                             * FORWARD epilogue (which has issue slots to spare) and saved instead of the pre-activation */
+  MTVAF_EPI_MUL_AUX = 10    /* out = acc * aux          (backward of :365-366 with aux = the saved gelu')            */
 };
 
 typedef struct MtvafEpilogue {

@@ -195,6 +195,21 @@ __device__ __forceinline__ float dgelu_fast(float x) {
   return fmaf(hs, du, fmaf(0.5f, t, 0.5f));
 }
 
+// gelu and its derivative from ONE tanh (MTVAF_EPI_GELU_GRAD: the derivative is saved by the forward epilogue)
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& d) {
+#ifdef MTVAF_GELU_EXACT
+  g = gelu_erf(x);
+  d = dgelu_erf(x);
+  return;
+#endif
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, 0.0356774081f, 0.7978845608f));
+  const float hx = 0.5f * x;
+  g = fmaf(hx, t, hx);
+  const float du = fmaf(x2, 0.1070322243f, 0.7978845608f);
+  d = fmaf(hx * fmaf(-t, t, 1.f), du, fmaf(0.5f, t, 0.5f));
+}
+
 // ---- dropout: counter-based hash RNG, recomputed (never stored) in backward ----------------------
 // keep(seed, stream, idx) is a pure function; `stream` separates the dropout sites of one step.
 __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {

@@ -41,11 +41,13 @@ inline int make_epi_args(const MtvafEpilogue& e, int operand_dtype, int M, int N
   o->colsum = e.colsum;
   o->step = step_source();
   o->drop_threshold = 0; o->drop_scale = 1.f;
-  MTVAF_REQUIRE(e.mode >= 0 && e.mode <= MTVAF_EPI_ROWSCALE, "bad epilogue mode %d", e.mode);
+  MTVAF_REQUIRE(e.mode >= 0 && e.mode <= MTVAF_EPI_MUL_AUX, "bad epilogue mode %d", e.mode);
   if (e.mode == MTVAF_EPI_ATOMIC_F32) o->out_bf16 = 0;
   if (e.mode != MTVAF_EPI_SQNORM) MTVAF_REQUIRE(e.out != nullptr, "epilogue: out is NULL");
-  if (e.mode == MTVAF_EPI_RESID || e.mode == MTVAF_EPI_MUL_DGELU || e.mode == MTVAF_EPI_MUL_DTANH)
+  if (e.mode == MTVAF_EPI_RESID || e.mode == MTVAF_EPI_MUL_DGELU || e.mode == MTVAF_EPI_MUL_DTANH ||
+      e.mode == MTVAF_EPI_MUL_AUX)
     MTVAF_REQUIRE(e.aux != nullptr, "epilogue mode %d needs aux", e.mode);
+  if (e.mode == MTVAF_EPI_GELU_GRAD) MTVAF_REQUIRE(e.out2 != nullptr, "epilogue GELU_GRAD needs out2");
   if (e.mode == MTVAF_EPI_SQNORM || e.mode == MTVAF_EPI_ROWSCALE)
     MTVAF_REQUIRE(e.rowvec != nullptr, "epilogue mode %d needs rowvec", e.mode);
   if (e.colsum)
@@ -105,6 +107,8 @@ __device__ __forceinline__ float epi_math(const EpiArgs& ep, float v, float a, i
   const int mode = (MODE >= 0) ? MODE : ep.mode;
   switch (mode) {
     case MTVAF_EPI_GELU: pre_out = v; return FAST ? gelu_fast(v) : gelu_erf(v);
+    case MTVAF_EPI_GELU_GRAD: pre_out = FAST ? dgelu_fast(v) : dgelu_erf(v); return FAST ? gelu_fast(v) : gelu_erf(v);
+    case MTVAF_EPI_MUL_AUX: return v * a;
     case MTVAF_EPI_TANH: return tanhf(v);
     case MTVAF_EPI_RESID:
       if (ep.drop_threshold) {
@@ -125,7 +129,8 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t
                                                int N, float& rowacc) {
   if (row >= M) return;
   const int mode = (MODE >= 0) ? MODE : ep.mode;
-  const bool needs_aux = (mode == MTVAF_EPI_RESID || mode == MTVAF_EPI_MUL_DGELU || mode == MTVAF_EPI_MUL_DTANH);
+  const bool needs_aux = (mode == MTVAF_EPI_RESID || mode == MTVAF_EPI_MUL_DGELU || mode == MTVAF_EPI_MUL_DTANH ||
+                          mode == MTVAF_EPI_MUL_AUX);
   const float rs = (mode == MTVAF_EPI_ROWSCALE) ? ep.rowvec[row] : 1.f;
   const bool full = (col0 + 32 <= N) && ep.vec_ok;
 #pragma unroll
@@ -159,7 +164,8 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t
           for (int j = 0; j < 8; ++j) rowacc += v[j] * v[j];
         }
         if (ep.out) epi_store8(ep.out, ep.out_bf16, (long long)row * ep.ldo + c, v);
-        if (mode == MTVAF_EPI_GELU && ep.out2) epi_store8(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + c, pre);
+        if ((mode == MTVAF_EPI_GELU || mode == MTVAF_EPI_GELU_GRAD) && ep.out2)
+          epi_store8(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + c, pre);
       }
     } else {
 #pragma unroll
@@ -175,7 +181,8 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& ep, const uint32_t
         } else {
           if (mode == MTVAF_EPI_SQNORM) rowacc += x * x;
           if (ep.out) epi_store(ep.out, ep.out_bf16, (long long)row * ep.ldo + cc, x);
-          if (mode == MTVAF_EPI_GELU && ep.out2) epi_store(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + cc, p);
+          if ((mode == MTVAF_EPI_GELU || mode == MTVAF_EPI_GELU_GRAD) && ep.out2)
+            epi_store(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + cc, p);
         }
       }
     }
@@ -191,7 +198,7 @@ __device__ __forceinline__ void epilogue_row_finish(const EpiArgs& ep, int row, 
 // element-wise form used by the SIMT fp32 GEMM
 __device__ __forceinline__ void epilogue_elem(const EpiArgs& ep, float acc, int row, int col, int N) {
   const bool needs_aux = (ep.mode == MTVAF_EPI_RESID || ep.mode == MTVAF_EPI_MUL_DGELU ||
-                          ep.mode == MTVAF_EPI_MUL_DTANH);
+                          ep.mode == MTVAF_EPI_MUL_DTANH || ep.mode == MTVAF_EPI_MUL_AUX);
   float x = acc * ep.alpha;
   if (ep.mode == MTVAF_EPI_ROWSCALE) x *= ep.rowvec[row];
   if (ep.bias) x += ep.bias[col];
@@ -204,7 +211,8 @@ __device__ __forceinline__ void epilogue_elem(const EpiArgs& ep, float acc, int 
   }
   if (ep.mode == MTVAF_EPI_SQNORM) atomicAdd(ep.rowvec + row, x * x);
   if (ep.out) epi_store(ep.out, ep.out_bf16, (long long)row * ep.ldo + col, x);
-  if (ep.mode == MTVAF_EPI_GELU && ep.out2) epi_store(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + col, p);
+  if ((ep.mode == MTVAF_EPI_GELU || ep.mode == MTVAF_EPI_GELU_GRAD) && ep.out2)
+    epi_store(ep.out2, ep.out_bf16, (long long)row * ep.ld_out2 + col, p);
 }
 
 }  // namespace mtvaf

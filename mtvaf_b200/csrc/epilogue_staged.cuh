@@ -16,9 +16,12 @@ template <int MODE>
 struct StagedEpi {
   static constexpr bool kStaged = (MODE == MTVAF_EPI_STORE || MODE == MTVAF_EPI_GELU || MODE == MTVAF_EPI_TANH ||
                                    MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU ||
-                                   MODE == MTVAF_EPI_MUL_DTANH);
-  static constexpr bool kAux = (MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU || MODE == MTVAF_EPI_MUL_DTANH);
-  static constexpr int kOutBufs = kStaged ? ((MODE == MTVAF_EPI_GELU) ? 2 : 1) : 0;
+                                   MODE == MTVAF_EPI_MUL_DTANH || MODE == MTVAF_EPI_GELU_GRAD ||
+                                   MODE == MTVAF_EPI_MUL_AUX);
+  static constexpr bool kAux = (MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU || MODE == MTVAF_EPI_MUL_DTANH ||
+                                MODE == MTVAF_EPI_MUL_AUX);
+  static constexpr bool kTwoOut = (MODE == MTVAF_EPI_GELU || MODE == MTVAF_EPI_GELU_GRAD);   // out + out2 boxes
+  static constexpr int kOutBufs = kStaged ? (kTwoOut ? 2 : 1) : 0;
 #ifndef MTVAF_EPI_AUX_BUFS
 // aux boxes per warp pair: 1 = the next box's operand is requested as soon as both warps have read the current one
 // (the operand ring gets the 32 KB back: 5 stages instead of 4 for RESID / xGELU' / xtanh'), 2 = prefetched two boxes
@@ -75,51 +78,10 @@ __device__ __forceinline__ void epi_load_bias32(const EpiArgs& ep, int col0, int
   }
 }
 
-// math of one 32-column chunk of one row: acc (TMEM registers) -> packed bf16 pairs.
-// bias: the 32 bias values (zeros when there is none); aux4: the thread's 4 x 16-byte pieces (32 bf16) of the
-// auxiliary operand, already in registers.
-template <int MODE>
-__device__ __forceinline__ void epi_compute32(const EpiArgs& ep, const uint32_t (&r)[32], const float (&bias)[32],
-                                              const uint4 (&aux4)[4], int row, int col0, int N, uint32_t (&outp)[16],
-                                              uint32_t (&prep)[16]) {
-  constexpr bool needs_aux = StagedEpi<MODE>::kAux;
-  uint32_t keep = 0xFFFFFFFFu;
-  if (MODE == MTVAF_EPI_RESID && ep.drop_threshold)
-    keep = dropout_mask32(ep.seed, (unsigned long long)row * (unsigned long long)N + col0, ep.drop_threshold);
-  const float alpha = ep.alpha;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float v[8], a[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), alpha, bias[g * 8 + j]);
-    if (needs_aux) {
-      const float2 a0 = unpack_bf16x2(aux4[g].x), a1 = unpack_bf16x2(aux4[g].y), a2 = unpack_bf16x2(aux4[g].z),
-                   a3 = unpack_bf16x2(aux4[g].w);
-      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
-    }
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = v[j];
-      if (MODE == MTVAF_EPI_GELU) o[j] = gelu_fast(x);
-      else if (MODE == MTVAF_EPI_TANH) o[j] = tanhf(x);
-      else if (MODE == MTVAF_EPI_RESID)
-        o[j] = ((keep >> (g * 8 + j)) & 1u) ? fmaf(x, ep.drop_scale, a[j]) : a[j];
-      else if (MODE == MTVAF_EPI_MUL_DGELU) o[j] = x * dgelu_fast(a[j]);
-      else if (MODE == MTVAF_EPI_MUL_DTANH) o[j] = x * (1.f - a[j] * a[j]);
-      else o[j] = x;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) outp[g * 4 + j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
-    if (MODE == MTVAF_EPI_GELU) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) prep[g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-    }
-  }
-}
-
-// Same math for NG groups of 8 consecutive columns (NG = 2: the 16-column steps of the 16-warp epilogue of the CTA-pair
-// kernel, which keeps its live registers under the 112 a 576-thread CTA allows).  keep: dropout keep bits, bit j = column j.
+// Math of NG groups of 8 consecutive columns of one row: acc (TMEM registers) -> packed bf16 pairs (NG = 2: the
+// 16-column steps of the 16-warp epilogue of the CTA-pair kernel, which keeps its live registers under the 112 a
+// 576-thread CTA allows).  bias: the bias values (zeros when there is none); aux4: the thread's 16-byte pieces of the
+// auxiliary operand, already in registers; keep: dropout keep bits, bit j = column j.
 template <int MODE, int NG>
 __device__ __forceinline__ void epi_compute_groups(const EpiArgs& ep, const uint32_t (&r)[8 * NG],
                                                    const float (&bias)[8 * NG], const uint4 (&aux4)[NG], uint32_t keep,
@@ -144,13 +106,15 @@ __device__ __forceinline__ void epi_compute_groups(const EpiArgs& ep, const uint
       else if (MODE == MTVAF_EPI_TANH) o[j] = tanhf(x);
       else if (MODE == MTVAF_EPI_RESID)
         o[j] = ((keep >> (g * 8 + j)) & 1u) ? fmaf(x, ep.drop_scale, a[j]) : a[j];
+      else if (MODE == MTVAF_EPI_GELU_GRAD) gelu_and_grad_fast(x, o[j], v[j]);   // v <- gelu'(x): the second output
       else if (MODE == MTVAF_EPI_MUL_DGELU) o[j] = x * dgelu_fast(a[j]);
       else if (MODE == MTVAF_EPI_MUL_DTANH) o[j] = x * (1.f - a[j] * a[j]);
+      else if (MODE == MTVAF_EPI_MUL_AUX) o[j] = x * a[j];
       else o[j] = x;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) outp[g * 4 + j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
-    if (MODE == MTVAF_EPI_GELU) {
+    if (StagedEpi<MODE>::kTwoOut) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) prep[g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
     }

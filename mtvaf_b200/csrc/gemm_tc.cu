@@ -62,7 +62,8 @@ extern "C" int mtvaf_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // optional column sums of the output: inside the TMA-staged epilogue of the CTA-pair kernel, else a pass over `out`
   const bool staged_mode = ep.mode == MTVAF_EPI_STORE || ep.mode == MTVAF_EPI_GELU || ep.mode == MTVAF_EPI_TANH ||
-                           ep.mode == MTVAF_EPI_RESID || ep.mode == MTVAF_EPI_MUL_DGELU || ep.mode == MTVAF_EPI_MUL_DTANH;
+                           ep.mode == MTVAF_EPI_RESID || ep.mode == MTVAF_EPI_MUL_DGELU || ep.mode == MTVAF_EPI_MUL_DTANH ||
+                           ep.mode == MTVAF_EPI_GELU_GRAD || ep.mode == MTVAF_EPI_MUL_AUX;
   const bool fused = ep.colsum && ep.staged && staged_mode && M >= 256 && gemm_impl_override() == 0;
   float* post = fused ? nullptr : ep.colsum;
   if (!fused) ep.colsum = nullptr;

@@ -334,7 +334,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int g = 0; g < 2; ++g) {
             const uint32_t off = box_piece_off(lane, part * 4 + g);
             st_shared_v4(out_a + off, o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
-            if (EPI == MTVAF_EPI_GELU)
+            if (SE::kTwoOut)
               st_shared_v4(out_a + kEpiBoxBytes + off, p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
           }
           if (SE::kAux) {
@@ -347,7 +347,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int g = 0; g < 2; ++g) {
             const uint32_t off = box_piece_off(lane, part * 4 + 2 + g);
             st_shared_v4(out_a + off, o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
-            if (EPI == MTVAF_EPI_GELU)
+            if (SE::kTwoOut)
               st_shared_v4(out_a + kEpiBoxBytes + off, p[g * 4], p[g * 4 + 1], p[g * 4 + 2], p[g * 4 + 3]);
           }
           fence_proxy_async_smem();                  // staging writes (and aux reads) ordered before the TMA ops
@@ -355,7 +355,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           named_bar_sync(bar_id, 64);                // both halves of the box staged, both warps done with the aux box
           if (issuer) {
             tma_store_2d(&tmOut, out_box, col0, row0);
-            if (EPI == MTVAF_EPI_GELU && ep.out2) tma_store_2d(&tmOut2, out_box + kEpiBoxBytes, col0, row0);
+            if (SE::kTwoOut && ep.out2) tma_store_2d(&tmOut2, out_box + kEpiBoxBytes, col0, row0);
             tma_store_commit();
             if (SE::kAux) {                          // refill the aux box just consumed with the box two ahead
               int r0n, c0n;
@@ -464,7 +464,7 @@ int launch_gemm_tc2(const void* A, int64_t lda, const void* B, int64_t ldb, int 
     // [32 rows x 64 cols] bf16 boxes of the output (and pre-activation / aux operands)
     rc = make_tmap_bf16_2d(&tmOut, epl.out, N, M, epl.ldo, 64, 32);
     if (rc) return rc;
-    if (EPI == MTVAF_EPI_GELU && epl.out2) {
+    if (SE::kTwoOut && epl.out2) {
       rc = make_tmap_bf16_2d(&tmOut2, epl.out2, N, M, epl.ld_out2, 64, 32);
       if (rc) return rc;
     }

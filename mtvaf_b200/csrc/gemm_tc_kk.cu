@@ -8,6 +8,7 @@ int gemm_tc_kk(const void* A, int64_t lda, const void* B, int64_t ldb, int M, in
   switch (ep.mode) {
     MTVAF_GEMM_CASE2(MTVAF_EPI_STORE, false, false);
     MTVAF_GEMM_CASE2(MTVAF_EPI_GELU, false, false);
+    MTVAF_GEMM_CASE2(MTVAF_EPI_GELU_GRAD, false, false);
     MTVAF_GEMM_CASE2(MTVAF_EPI_TANH, false, false);
     MTVAF_GEMM_CASE2(MTVAF_EPI_RESID, false, false);
     MTVAF_GEMM_CASE2(MTVAF_EPI_SQNORM, false, false);

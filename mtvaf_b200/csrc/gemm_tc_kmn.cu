@@ -10,6 +10,7 @@ int gemm_tc_kmn(const void* A, int64_t lda, const void* B, int64_t ldb, int M, i
     MTVAF_GEMM_CASE2(MTVAF_EPI_RESID, false, true);
     MTVAF_GEMM_CASE2(MTVAF_EPI_MUL_DGELU, false, true);
     MTVAF_GEMM_CASE2(MTVAF_EPI_MUL_DTANH, false, true);
+    MTVAF_GEMM_CASE2(MTVAF_EPI_MUL_AUX, false, true);
     default:
       return narrow ? launch_gemm_tc<128, false, true, -1>(A, lda, B, ldb, M, N, K, ep, splits, stream)
                     : launch_gemm_tc<256, false, true, -1>(A, lda, B, ldb, M, N, K, ep, splits, stream);

@@ -304,9 +304,12 @@ class Engine:
                                 seed=self.seed(16 * i + 3))
             a, m1, r1 = ops.layernorm_fwd(z1, f.w(ln("attention.output.LayerNorm.weight")),
                                           f.w(ln("attention.output.LayerNorm.bias")), c.eps)
+            # training: the forward epilogue also computes gelu'(pre) -- it has issue slots to spare, the backward
+            # epilogue that would otherwise recompute it from the pre-activation does not (profiles/r2_ncu_hot_b512.md)
+            # -- and `pre` holds that derivative instead of the pre-activation
             pre = torch.empty((B * Lq, c.I), dtype=cd, device=x.device) if save else None
             g = ops.linear_fwd(a, self.cw(ln("intermediate.dense.weight")), f.w(ln("intermediate.dense.bias")),
-                               mode=L.EPI_GELU, out2=pre)
+                               mode=L.EPI_GELU_GRAD if save else L.EPI_GELU, out2=pre)
             z2 = ops.linear_fwd(g, self.cw(ln("output.dense.weight")), f.w(ln("output.dense.bias")),
                                 mode=L.EPI_RESID, aux=a, p_drop=p_h, seed=self.seed(16 * i + 4))
             y, m2, r2 = ops.layernorm_fwd(z2, f.w(ln("output.LayerNorm.weight")), f.w(ln("output.LayerNorm.bias")),
@@ -366,7 +369,7 @@ class Engine:
                                          d_bias=f.g(ln("output.dense.bias")), p_drop=p_h, seed=sd(16 * i + 4))
             ops.linear_wgrad(dd2, s["g"], f.g(ln("output.dense.weight")))
             # (d(intermediate.dense.bias) = column sums of dpre: summed from the staging boxes of this GEMM's epilogue)
-            dpre = ops.linear_dgrad(dd2, self.cw(ln("output.dense.weight")), mode=L.EPI_MUL_DGELU, aux=s["pre"],
+            dpre = ops.linear_dgrad(dd2, self.cw(ln("output.dense.weight")), mode=L.EPI_MUL_AUX, aux=s["pre"],
                                     colsum=f.g(ln("intermediate.dense.bias")))
             # ---- intermediate: g = gelu(a W1^T + b1)
             ops.linear_wgrad(dpre, s["a"], f.g(ln("intermediate.dense.weight")))

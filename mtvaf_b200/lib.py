@@ -15,7 +15,8 @@ if os.environ.get("MTVAF_LIB_TAG"):          # experiment builds (mtvaf_b200/bui
 
 F32, BF16 = 0, 1
 
-EPI_STORE, EPI_GELU, EPI_TANH, EPI_RESID, EPI_ATOMIC_F32, EPI_MUL_DGELU, EPI_MUL_DTANH, EPI_SQNORM, EPI_ROWSCALE = range(9)
+(EPI_STORE, EPI_GELU, EPI_TANH, EPI_RESID, EPI_ATOMIC_F32, EPI_MUL_DGELU, EPI_MUL_DTANH, EPI_SQNORM, EPI_ROWSCALE,
+ EPI_GELU_GRAD, EPI_MUL_AUX) = range(11)
 
 
 class MtvafError(RuntimeError):

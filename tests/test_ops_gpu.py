@@ -100,6 +100,10 @@ def test_gemm_fused_column_sums(ops, Lb, dtype, M, N, K):
     assert rel_err(cs - base, ref) < (2e-3 if dtype == torch.bfloat16 else 2e-5)
     out2 = ops.gemm(dy, w, b_mn=True, M=M, N=N, K=K, mode=Lb.EPI_MUL_DGELU, aux=aux)
     assert torch.equal(out, out2)
+    cs3 = base.clone()                                                      # the training path's form: x * saved gelu'
+    out3 = ops.gemm(dy, w, b_mn=True, M=M, N=N, K=K, mode=Lb.EPI_MUL_AUX, aux=aux, colsum=cs3)
+    assert rel_err(out3, (dy.float() @ w.float()) * aux.float()) < (1.5e-2 if dtype == torch.bfloat16 else 3e-5)
+    assert rel_err(cs3 - base, out3.float().sum(0)) < (2e-3 if dtype == torch.bfloat16 else 2e-5)
     cs2 = torch.zeros(N, device=DEV)
     bias = rnd(N, seed=35)
     y = ops.linear_fwd(dy, w.t().contiguous(), bias, colsum=cs2)          # STORE + bias: rows past M must not count
@@ -162,6 +166,15 @@ def test_gemm_epilogues(ops, Lb, dtype):
     pf = pre_in.float().requires_grad_()
     F.gelu(pf).sum().backward()
     assert rel_err(dg, (base - bias) * pf.grad) < tol
+    # GELU with the DERIVATIVE as side output (saved by the forward epilogue), and the plain x * aux backward epilogue
+    dpre = torch.empty(M, N, dtype=dtype, device=DEV)
+    g2 = ops.linear_fwd(x, w, bias, mode=Lb.EPI_GELU_GRAD, out2=dpre)
+    bf = base.clone().requires_grad_()
+    F.gelu(bf).sum().backward()
+    assert rel_err(g2, F.gelu(base)) < tol
+    assert rel_err(dpre, bf.grad) < tol
+    ma = ops.linear_fwd(x, w, None, mode=Lb.EPI_MUL_AUX, aux=pre_in)
+    assert rel_err(ma, (base - bias) * pre_in.float()) < tol
     # dtanh multiply
     th = torch.tanh(rnd(M, N, seed=12)).to(dtype)
     dth = ops.linear_fwd(x, w, None, mode=Lb.EPI_MUL_DTANH, aux=th)

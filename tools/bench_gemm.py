@@ -48,6 +48,8 @@ def main():
             t["dgrad"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx))
             pre = torch.randn(M, K, device="cuda").bfloat16()
             t["dgrad_dgelu"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx, mode=Lb.EPI_MUL_DGELU, aux=pre))
+            t["fwd_gelu_grad"] = timeit(lambda: ops.linear_fwd(x, w, bias, out=out, mode=Lb.EPI_GELU_GRAD, out2=out2))
+            t["dgrad_mulaux"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx, mode=Lb.EPI_MUL_AUX, aux=pre))
             t["dgrad_resid"] = timeit(lambda: ops.gemm(dy, w, b_mn=True, M=M, N=K, K=N, out=dx, mode=Lb.EPI_RESID, aux=pre))
             t["wgrad"] = timeit(lambda: ops.linear_wgrad(dy, x, dw))
             for k, v in t.items():

@@ -61,6 +61,9 @@ def main():
         ("ffn2_dgrad_dgelu", lambda: ops.gemm(x, w_2, b_mn=True, M=T, N=4 * H, K=H, out=o_i, mode=Lb.EPI_MUL_DGELU, aux=o_i2)),
         ("ffn2_dgrad_dgelu_colsum", lambda: ops.gemm(x, w_2, b_mn=True, M=T, N=4 * H, K=H, out=o_i, mode=Lb.EPI_MUL_DGELU,
                                                      aux=o_i2, colsum=dbias_i)),
+        ("ffn1_fwd_gelu_grad", lambda: ops.linear_fwd(x, w_1, b_i, out=o_i, mode=Lb.EPI_GELU_GRAD, out2=o_i2)),
+        ("ffn2_dgrad_mulaux_colsum", lambda: ops.gemm(x, w_2, b_mn=True, M=T, N=4 * H, K=H, out=o_i, mode=Lb.EPI_MUL_AUX,
+                                                      aux=o_i2, colsum=dbias_i)),
         ("ffn1_dgrad_resid", lambda: ops.gemm(xi, w_1, b_mn=True, M=T, N=H, K=4 * H, out=o_h, mode=Lb.EPI_RESID, aux=x)),
         ("attn_out_dgrad_store", lambda: ops.gemm(x, w_o, b_mn=True, M=T, N=H, K=H, out=o_h)),
         ("ffn1_wgrad", lambda: ops.linear_wgrad(xi, x, dw)),

@@ -15,7 +15,7 @@ COLS = [("gpu__time_duration.sum", "us"), ("sm__pipe_tensor_cycles_active.avg.pc
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "long scoreboard / issue")]
 FLOPS = {"qkv_fwd_store": (2304, 768), "ffn1_fwd_gelu": (3072, 768), "attn_out_fwd_resid": (768, 768),
          "ffn2_fwd_resid": (768, 3072), "ffn2_dgrad_dgelu": (3072, 768), "ffn2_dgrad_dgelu_colsum": (3072, 768),
-         "ffn1_dgrad_resid": (768, 3072), "attn_out_dgrad_store": (768, 768), "ffn1_wgrad": (3072, 768)}
+         "ffn1_dgrad_resid": (768, 3072), "ffn1_fwd_gelu_grad": (3072, 768), "ffn2_dgrad_mulaux_colsum": (3072, 768), "attn_out_dgrad_store": (768, 768), "ffn1_wgrad": (3072, 768)}
 
 
 def num(s, unit_scale=None):
