@@ -100,6 +100,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int row8 = row & 7;
   const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
   const int units = a.N16 >> 3;
+  const uint32_t aMask = smem_u32(sMask), aPs = smem_u32(sP), aExch = smem_u32(sExch);   // explicit shared-space accesses
 
   // key `k` of batch row `b` -> additive mask; keys >= N16 are never read (N16 <= 448 < kFwdThreads)
   auto fetch_mask = [&](int b, int k) -> float {
@@ -157,19 +158,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int c = u << 3;
       uint32_t r[8];
       tmem_ld_32x32b_x8(t_row + c, r);
-      const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
-      const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
+      const float4 m0 = lds_f4(aMask + c * 4);
+      const float4 m1 = lds_f4(aMask + c * 4 + 16);
       tmem_ld_wait();
       mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[0]), sc2, m0.x), fmaf(__uint_as_float(r[1]), sc2, m0.y)),
                            fmaxf(fmaf(__uint_as_float(r[2]), sc2, m0.z), fmaf(__uint_as_float(r[3]), sc2, m0.w))));
       mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[4]), sc2, m1.x), fmaf(__uint_as_float(r[5]), sc2, m1.y)),
                            fmaxf(fmaf(__uint_as_float(r[6]), sc2, m1.z), fmaf(__uint_as_float(r[7]), sc2, m1.w))));
     }
-    sExch[half * 128 + row] = mx;
+    sts_f32(aExch + (half * 128 + row) * 4, mx);
     __syncthreads();
     // finite: key 0 exists and S is finite (a part without units contributes -inf)
-    float mx2 = fmaxf(sExch[row], sExch[128 + row]);
-    if (NPART == 4) mx2 = fmaxf(mx2, fmaxf(sExch[256 + row], sExch[384 + row]));
+    float mx2 = fmaxf(lds_f32(aExch + row * 4), lds_f32(aExch + (128 + row) * 4));
+    if (NPART == 4) mx2 = fmaxf(mx2, fmaxf(lds_f32(aExch + (256 + row) * 4), lds_f32(aExch + (384 + row) * 4)));
 
     // ---- pass 2: P = exp2(x - max), row sum, dropout, bf16 P -> shared memory.  With dropout the 1/(1-p) scale
     // rides in the exponent (max - log2(scale)): P is born scaled, the row sum is corrected once at the end.
@@ -181,8 +182,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int c = u << 3;
       uint32_t r[8];
       tmem_ld_32x32b_x8(t_row + c, r);
-      const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
-      const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
+      const float4 m0 = lds_f4(aMask + c * 4);
+      const float4 m1 = lds_f4(aMask + c * 4 + 16);
       const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
       tmem_ld_wait();
       float p[8];
@@ -195,9 +196,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint4 w;
       w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
       w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
-      *reinterpret_cast<uint4*>(sP + (u >> 3) * 16384 + prow_off + (((u & 7) ^ row8) << 4)) = w;
+      sts_u4(aPs + (u >> 3) * 16384 + prow_off + (((u & 7) ^ row8) << 4), w);
     }
-    sExch[512 + half * 128 + row] = sum;
+    sts_f32(aExch + (512 + half * 128 + row) * 4, sum);
     fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -216,8 +217,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(&bars[2]);
     }
     __syncwarp();
-    float total = sExch[512 + row] + sExch[640 + row];
-    if (NPART == 4) total += sExch[768 + row] + sExch[896 + row];
+    float total = lds_f32(aExch + (512 + row) * 4) + lds_f32(aExch + (640 + row) * 4);
+    if (NPART == 4) total += lds_f32(aExch + (768 + row) * 4) + lds_f32(aExch + (896 + row) * 4);
     mbar_wait(&bars[2], ph);
     __syncwarp();
     tc_fence_after();

@@ -126,6 +126,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t aMask = smem_u32(sMask), aPs = smem_u32(sP), adSs = smem_u32(sdS);   // explicit shared-space accesses
 
   const uint32_t kv_bytes = (uint32_t)loaded_rows * 128u;
   auto load_qk = [&](int item, int buf) {              // one thread
@@ -273,8 +274,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t rs[8], rd[8];
       tmem_ld_32x32b_x8(t_row + c, rs);
       tmem_ld_32x32b_x8(t_row + DP_COL + c, rd);
-      const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
-      const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
+      const float4 m0 = lds_f4(aMask + (c) * 4);
+      const float4 m1 = lds_f4(aMask + (c) * 4 + 16);
       const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
       tmem_ld_wait();
       float p[8], dp[8], ds[8];
@@ -292,10 +293,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint4 w;
       w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
       w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
-      *reinterpret_cast<uint4*>(sP + off) = w;
+      sts_u4(aPs + off, w);
       w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
       w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
-      *reinterpret_cast<uint4*>(sdS + off) = w;
+      sts_u4(adSs + off, w);
     }
     // key columns [N16, 64*n_chunks) of the last chunk are read by the key-tile MMAs as rows that are never
     // stored; they need no initialisation (TMEM lanes are independent).

@@ -108,6 +108,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t aMask = smem_u32(sMask), aPs = smem_u32(sP), adSs = smem_u32(sdS);   // explicit shared-space accesses
 
   const bool has_prefix = a.P8 > 0;
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -227,8 +228,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t rs[8], rd[8];
           tmem_ld_32x32b_x8(t_row + LC_S + c, rs);
           tmem_ld_32x32b_x8(t_row + LC_DP + c, rd);
-          const float4 m0 = *reinterpret_cast<const float4*>(sMask + kb * 128 + c);
-          const float4 m1 = *reinterpret_cast<const float4*>(sMask + kb * 128 + c + 4);
+          const float4 m0 = lds_f4(aMask + (kb * 128 + c) * 4);
+          const float4 m1 = lds_f4(aMask + (kb * 128 + c) * 4 + 16);
           const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           tmem_ld_wait();
           float p[8], dp[8], ds[8];
@@ -247,10 +248,10 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint4 w;
           w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
           w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(sP + off) = w;
+          sts_u4(aPs + off, w);
           w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
           w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
-          *reinterpret_cast<uint4*>(sdS + off) = w;
+          sts_u4(adSs + off, w);
         }
         // key columns [NB, 128) of a short block keep older (finite) values: they only feed accumulator rows of
         // dK / dV that are never stored, and the dQ contraction stops at NB

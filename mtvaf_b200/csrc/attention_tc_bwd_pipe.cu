@@ -254,7 +254,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float acc = 0.f;
       if (row_ok) {
         const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)b * a.L + row) * ld_ctx + h * 64);
-        const uint8_t* pd = sdO0 + buf * 16384 + prow_off;
+        const uint32_t pd = smem_u32(sdO0) + buf * 16384 + prow_off;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {                 // two batches of four 16-byte loads (drain warps have slack)
           uint4 o[4];
@@ -262,7 +262,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int c = 0; c < 4; ++c) o[c] = __ldg(po + hf * 4 + c);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint4 dv = *reinterpret_cast<const uint4*>(pd + (((hf * 4 + c) ^ row8) << 4));
+            const uint4 dv = lds_u4(pd + (((hf * 4 + c) ^ row8) << 4));
             const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
             const uint32_t ow[4] = {o[c].x, o[c].y, o[c].z, o[c].w};
 #pragma unroll
@@ -274,7 +274,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       }
-      sD0[buf * 128 + row] = acc;
+      sts_f32(smem_u32(sD0) + (buf * 128 + row) * 4, acc);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_d[buf]);
     };
@@ -399,7 +399,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       simt_barrier();                                    // publishes sMask
       // dS = P' (scale / drop_scale) (drop_scale dP_raw - D) = P' * scale * (dP_raw - D / drop_scale)
       mbar_wait(&bar_d[buf], ph2);                       // D_q of this item (drain warps, one item ahead)
-      const float dsum_s = sD0[buf * 128 + row] / a.drop_scale;
+      const float dsum_s = lds_f32(smem_u32(sD0) + (buf * 128 + row) * 4) / a.drop_scale;
       const float ds_c = a.scale;
       const uint32_t rowkey =
           a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
@@ -409,10 +409,11 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ---- P and dS for this thread's (row, every 4th 8-key unit).  P' = P / (1-p) is born scaled (the dropout
       // scale rides in the exponent: lse2 carries -log2(scale)); dropped keys are zeroed in P' and in dP.
       // The TMEM loads of the NEXT unit are in flight while the current one is processed (ping-pong registers).
+      const uint32_t aMask = smem_u32(sMask), aP = smem_u32(sP), adS = smem_u32(sdS);
       auto process_unit = [&](int u, const uint32_t (&rs)[8], const uint32_t (&rd)[8]) {
         const int c = u << 3;
-        const float4 m0 = *reinterpret_cast<const float4*>(sMask + c);
-        const float4 m1 = *reinterpret_cast<const float4*>(sMask + c + 4);
+        const float4 m0 = lds_f4(aMask + c * 4);
+        const float4 m1 = lds_f4(aMask + c * 4 + 16);
         const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
         float p[8], dp[8], ds[8];
 #pragma unroll
@@ -430,10 +431,10 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint4 w;
         w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
         w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(sP + off) = w;
+        sts_u4(aP + off, w);
         w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
         w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
-        *reinterpret_cast<uint4*>(sdS + off) = w;
+        sts_u4(adS + off, w);
       };
       {
         uint32_t sa[8], da[8], sb[8], db[8];
