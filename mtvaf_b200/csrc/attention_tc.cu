@@ -16,6 +16,7 @@
 //   store: O / rowsum -> ctx (heads merged, :276-278; 64 B per thread), lse = max + log(rowsum) for backward.
 // The backward kernel (same tiling, five MMAs) is in attention_tc_bwd.cu.
 #include "attention_tc.cuh"
+#include <cstdlib>
 #include <algorithm>
 
 namespace mtvaf {
@@ -294,7 +295,9 @@ int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int6
       MTVAF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       set0 = true;
     }
-    const int per_sm = 2 * smem <= 227 * 1024 ? 2 : 1;
+    int per_sm = 2 * smem <= 227 * 1024 ? 2 : 1;
+    static const char* env_ps = getenv("MTVAF_ATTN_FWD_CTAS_PER_SM");      // experiment knob
+    if (env_ps && atoi(env_ps) == 1) per_sm = 1;
     const int grid = n_items < per_sm * sm_count() ? n_items : per_sm * sm_count();
     attn_fwd_tc_kernel<false><<<grid, kFwdThreadsSmall, smem, st>>>(m.q, m.kv, m.kp, m.vp, a, (__nv_bfloat16*)ctx, ld_ctx, lse);
   } else {
