@@ -21,7 +21,11 @@ struct StagedEpi {
   static constexpr bool kAux = (MODE == MTVAF_EPI_RESID || MODE == MTVAF_EPI_MUL_DGELU || MODE == MTVAF_EPI_MUL_DTANH ||
                                 MODE == MTVAF_EPI_MUL_AUX);
   static constexpr bool kTwoOut = (MODE == MTVAF_EPI_GELU || MODE == MTVAF_EPI_GELU_GRAD);   // out + out2 boxes
-  static constexpr int kOutBufs = kStaged ? (kTwoOut ? 2 : 1) : 0;
+#ifndef MTVAF_EPI_INPLACE
+#define MTVAF_EPI_INPLACE 0                // 1: the aux variants write their results INTO the aux box and store from it
+#endif                                     //    (no separate staging box: one more operand-ring stage; the next aux load waits for the store)
+  static constexpr bool kInplace = kAux && (MTVAF_EPI_INPLACE != 0);
+  static constexpr int kOutBufs = kStaged ? (kInplace ? 0 : (kTwoOut ? 2 : 1)) : 0;
 #ifndef MTVAF_EPI_AUX_BUFS
 // aux boxes per warp pair: 1 = the next box's operand is requested as soon as both warps have read the current one
 // (the operand ring gets the 32 KB back: 5 stages instead of 4 for RESID / xGELU' / xtanh'), 2 = prefetched two boxes

@@ -306,7 +306,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int c32 = col0 + part * 32;          // this warp's 32 columns
           const uint32_t ab = kAB == 2 ? (used & 1) : 0;
           const uint32_t ab_phase = kAB == 2 ? ((used >> 1) & 1) : (used & 1);
-          const uint32_t out_a = smem_u32(out_box), aux_a = smem_u32(aux_box) + ab * kEpiBoxBytes;
+          const uint32_t aux_a = smem_u32(aux_box) + ab * kEpiBoxBytes;
+          const uint32_t out_a = SE::kInplace ? aux_a : smem_u32(out_box);
           // two 16-column steps; the TMEM load and the bias of step 1 are in flight while step 0 is computed
           uint32_t ra[16], rb[16];
           tmem_ld_32x32b_x16(t_addr + j * 64 + part * 32, ra);
@@ -326,10 +327,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           epi_load_bias16(ep, c32 + 16, N, c32 + 32 <= N, bias_b);
           uint32_t o[8], p[8];
           epi_compute_groups<EPI, 2>(ep, ra, bias_a, aux2, keep, o, p);
-          // the pair's staging box is free once the previous TMA store has finished READING it
-          if (issuer) tma_store_wait_read<0>();
-          __syncwarp();
-          named_bar_sync(bar_id, 64);
+          if (!SE::kInplace) {
+            // the pair's staging box is free once the previous TMA store has finished READING it
+            if (issuer) tma_store_wait_read<0>();
+            __syncwarp();
+            named_bar_sync(bar_id, 64);
+          }                                          // (in place: each thread overwrites exactly the aux pieces it read)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const uint32_t off = box_piece_off(lane, part * 4 + g);
@@ -354,10 +357,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
           named_bar_sync(bar_id, 64);                // both halves of the box staged, both warps done with the aux box
           if (issuer) {
-            tma_store_2d(&tmOut, out_box, col0, row0);
+            tma_store_2d(&tmOut, SE::kInplace ? aux_box + ab * kEpiBoxBytes : out_box, col0, row0);
             if (SE::kTwoOut && ep.out2) tma_store_2d(&tmOut2, out_box + kEpiBoxBytes, col0, row0);
             tma_store_commit();
-            if (SE::kAux) {                          // refill the aux box just consumed with the box two ahead
+            if (SE::kAux && !SE::kInplace) {         // refill the aux box just consumed with the next box
               int r0n, c0n;
               if (pf_next(r0n, c0n)) {
                 mbar_arrive_expect_tx(&my_bar[ab], kEpiBoxBytes);
@@ -394,6 +397,23 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               if (cc < N) atomicAdd(ep.colsum + cc, s0);
               if (cc + 1 < N) atomicAdd(ep.colsum + cc + 1, s1);
             }
+          }
+          if (SE::kInplace) {
+            // the box is both the store's source and the next aux load's destination: the load is issued once the store
+            // has finished reading it (and, with colsum, once both warps have read their column sums out of it)
+            if (ep.colsum) {
+              __syncwarp();
+              named_bar_sync(bar_id, 64);
+            }
+            if (issuer) {
+              int r0n, c0n;
+              if (pf_next(r0n, c0n)) {
+                tma_store_wait_read<0>();
+                mbar_arrive_expect_tx(&my_bar[ab], kEpiBoxBytes);
+                tma_load_2d(aux_box + ab * kEpiBoxBytes, &tmAux, &my_bar[ab], c0n, r0n);
+              }
+            }
+            __syncwarp();
           }
           ++used;
         }
