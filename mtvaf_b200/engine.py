@@ -240,6 +240,31 @@ class Engine:
         if self.bf16:
             self.flat.refresh_bf16()
 
+    def _forked(self, n: int):
+        """Context manager: `n` cached side streams that wait for the current stream on entry (fork) and that the current
+        stream waits for on exit (join).  Tensors touched inside must outlive the join (they do: saved activations /
+        function-scope buffers)."""
+        eng = self
+        if not hasattr(self, "_side_streams"):
+            self._side_streams = []
+        dev = self.flat.device
+
+        class _Fork:
+            def __enter__(self_):
+                while len(eng._side_streams) < n:
+                    eng._side_streams.append(torch.cuda.Stream(device=dev))
+                self_.cur = torch.cuda.current_stream(dev)
+                self_.streams = eng._side_streams[:n]
+                for st in self_.streams:
+                    st.wait_stream(self_.cur)
+                return self_.streams
+
+            def __exit__(self_, *exc):
+                for st in self_.streams:
+                    self_.cur.wait_stream(st)
+                return False
+        return _Fork()
+
     def new_step(self):
         """Advance the dropout step counter -- once per outermost forward entry point (a wrapping model's forward
         marks its nested encoder / fusion calls with `_nested`)."""
@@ -456,9 +481,13 @@ class Engine:
             ld = (n_anp + 7) // 8 * 8
             logits = torch.zeros((rows, ld), dtype=F32, device=x.device)
             names = ["img_classifier"] + ["aux_img_classifier.%d" % k for k in range(n_img - 1)]
-            for j, nm in enumerate(names):
-                ops.gemm(gmd[j * B:(j + 1) * B], self.cw(nm + ".weight"), M=B, N=n_anp, K=W8,
-                         bias=f.w(nm + ".bias"), out=logits[j * B:(j + 1) * B], ldo=ld)
+            # the ANP heads are independent M = B GEMMs that fill a quarter of the GPU each (18 CTA pairs at B = 512):
+            # issued on side streams they run side by side (fork / join; captured as parallel branches of the graph)
+            with self._forked(len(names)) as streams:
+                for j, nm in enumerate(names):
+                    with torch.cuda.stream(streams[j]):
+                        ops.gemm(gmd[j * B:(j + 1) * B], self.cw(nm + ".weight"), M=B, N=n_anp, K=W8,
+                                 bias=f.w(nm + ".bias"), out=logits[j * B:(j + 1) * B], ldo=ld)
             img_losses, dlogits = ops.softmax_kl(logits, n_anp, imagelabel, B, save)
             saved.update(gmd=gmd, dlogits=dlogits, names=names, n_anp=n_anp, p_i=p_i, seed_i=self.seed(900))
         gs = ops.mean4_fwd(guids, rows, W8, 1)                                                   # [rows, 8H]
@@ -518,11 +547,14 @@ class Engine:
                 ops.scale_by_device_scalar(dlog[j * B:(j + 1) * B], d_img_losses[j:j + 1])
             dl = ops.cast_bf16(dlog) if cd == BF16 else dlog
             d_gmd = torch.empty((rows, W8), dtype=cd, device=guids.device)
-            for j, nm in enumerate(saved["names"]):
-                dj = dl[j * B:(j + 1) * B]
-                ops.linear_wgrad(dj, saved["gmd"][j * B:(j + 1) * B], f.g(nm + ".weight"), n_valid=n_anp)
-                ops.colsum(dj, f.g(nm + ".bias"), n_valid=n_anp)
-                ops.gemm(dj, self.cw(nm + ".weight"), b_mn=True, M=B, N=W8, K=n_anp, out=d_gmd[j * B:(j + 1) * B])
+            with self._forked(len(saved["names"])) as streams:
+                for j, nm in enumerate(saved["names"]):
+                    with torch.cuda.stream(streams[j]):
+                        dj = dl[j * B:(j + 1) * B]
+                        ops.gemm(dj, self.cw(nm + ".weight"), b_mn=True, M=B, N=W8, K=n_anp,
+                                 out=d_gmd[j * B:(j + 1) * B])
+                        ops.linear_wgrad(dj, saved["gmd"][j * B:(j + 1) * B], f.g(nm + ".weight"), n_valid=n_anp)
+                        ops.colsum(dj, f.g(nm + ".bias"), n_valid=n_anp)
             p_i, seed_i = saved["p_i"], saved["seed_i"]
         # gate path + both 4-way-mean backward terms (+ img_dropout mask) in one pass, in the GEMM dtype
         dg = ops.prompt_grad_combine(d_guids, d_gs, d_gmd, p_i, seed_i, rows, W8, cd)

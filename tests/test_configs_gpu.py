@@ -198,3 +198,42 @@ def test_sweep_probes(layer, Lq):
     # pseudo labels from the depth norms: integer-valued, bit-exact against the restated rule
     lab = ops.probe_labels(norms)
     assert torch.equal(lab.cpu(), O.construct_label(norms.cpu()))
+
+
+# ------------------------------------------------------------------------------------------------ --use_align long text
+@pytest.mark.parametrize("dtype,tol,gtol", [("fp32", 1e-4, 5e-3), ("bf16", 2e-2, 8e-2)])
+def test_tvnet2_long_aligned_text_l500_matches_oracle(dtype, tol, gtol):
+    """The reference's `--use_align` inputs: caption + OCR + face + ANP text concatenated behind the tweet, up to
+    max_seq_agn = 500 tokens (MTVAF_training.py:250,342-348; modules/dataset.py:241-261), through the whole
+    TVNetSAModel2 with the visual prefix (P = 16).  In bf16 this is the long-text tcgen05 path end to end: forward as two
+    key windows + merge (16 + 500 keys do not fit one resident tile set), backward with two query-tile groups."""
+    from types import SimpleNamespace
+    from mtvaf_b200.modules import TVNetSAModel2, FeatureStub
+    cfg = O.EncoderCfg.roberta_base(vocab_size=1500)
+    B, Lq = 2, 500
+    params = S.init_params(cfg, seed=51, ln_jitter=0.05)
+    batch = S.make_batch(B, Lq, vocab=cfg.vocab_size, shape="longaux", seed=52)
+    batch["attention_mask"][0, 470:] = 0                      # ragged: one sequence shorter than the other
+    batch["input_ids"][0, 470:] = 0
+    batch["labels"][0, 469] = 10
+    batch["labels"][0, 470:] = 0
+    p = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in params.items()}
+    o = O.tvnet2_forward(p, cfg, batch, alpha=0.1, beta=0.5)
+    o["loss"].backward()
+    args = SimpleNamespace(bert_name="roberta-base", prefix_dim=768, prefix_len=4, use_prefix=True, use_probe=True, beta=0.5,
+                           alpha=0.1, vao=True, noauxloss=False, resnet_root=None, compute_dtype=dtype, probe_ckpt="")
+    m = TVNetSAModel2(list(range(10)), None, args, config=hf_config(cfg), image_model=FeatureStub())
+    m.load_state_dict(params, strict=False)
+    m = m.to(DEV).eval()
+    out, prob, img = m(**{k: v.to(DEV) for k, v in batch.items()})
+    assert rel(out.loss, o["loss"]) < tol
+    assert rel(m.last_emissions, o["emissions"]) < tol
+    assert rel(prob, o["prob_loss"]) < tol
+    if dtype == "fp32":
+        assert out.logits == o["logits"]
+    out.loss.backward()
+    for name in ("bert.encoder.layer.11.attention.self.value.weight", "bert.encoder.layer.0.attention.self.key.weight",
+                 "bert.encoder.layer.5.intermediate.dense.weight", "encoder_conv.2.weight", "fc.weight"):
+        got = dict(m.named_parameters())[name].grad.cpu()
+        ref = p[name].grad
+        assert float((got - ref).norm() / ref.norm()) < gtol, name
