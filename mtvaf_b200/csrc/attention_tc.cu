@@ -278,6 +278,234 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ---- short text (L <= 64): TWO (batch, head) items per 128-row tile -------------------------------------------------
+// A 128-row tile holds only L <= 64 query rows of one item: half the TMEM lanes (= half the softmax threads) would work
+// on rows nobody stores.  Here rows [0, 64) belong to item 2i and rows [64, 128) to item 2i + 1; the keys of the two
+// items are laid end to end (KR = P8 + 64 smem rows each), S = [Q_a; Q_b] [K_a; K_b]^T is ONE M = 128, N = 2 KR MMA whose
+// off-diagonal blocks are simply never read, and P is block diagonal -- its off-diagonal pieces in shared memory are
+// zeroed once per CTA and never written again -- so O = P [V_a; V_b] is again one MMA.  The tensor pipe does twice the
+// useful flops (it idles at < 10 % either way); every softmax thread now works on a row that exists.
+__global__ void __launch_bounds__(kFwdThreadsSmall, 2)
+attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKp,
+                        const __grid_constant__ CUtensorMap tmVp, AttnTcArgs a, __nv_bfloat16* __restrict__ ctx,
+                        long long ld_ctx, float* __restrict__ lse_out) {
+  constexpr int S_COLS = 192, TMEM_COLS = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KR = a.P8 + 64;                          // key rows (= S columns) per item
+  const int n_keys = 2 * KR;                         // multiple of 16
+  const int n_chunks = (n_keys + 63) / 64;
+  uint8_t* sQ = smem;                                // [128][64] bf16: rows [0,64) item a, [64,128) item b
+  uint8_t* sK = sQ + 16384;                          // [2 KR][64]
+  uint8_t* sV = sK + n_keys * 128;
+  uint8_t* sP = sV + n_keys * 128;                   // n_chunks x [128][64] bf16, block diagonal
+  float* sMask = reinterpret_cast<float*>(sP + n_chunks * 16384);     // [2 KR]
+  float* sExch = sMask + ((n_keys + 15) / 16) * 16;  // [2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 512);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const int blk = quad >> 1;                         // which item of the pair this row belongs to (warp-uniform)
+  const int H = a.nh * 64;
+  const int n_bh = a.B * a.nh;
+  const int n_items = (n_bh + 1) / 2;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmKV);
+    if (a.P8 > 0) { prefetch_tmap(&tmKp); prefetch_tmap(&tmVp); }
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  // P starts as zeros: the off-diagonal pieces stay that way for the life of the CTA
+  for (int i = tid; i < n_chunks * 1024; i += kFwdThreadsSmall) sts_u4(smem_u32(sP) + i * 16, make_uint4(0, 0, 0, 0));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // an odd item count leaves the last pair with one item: its second half re-reads the first (never stored)
+  auto bh_of = [&](int item, int j) { const int bh = 2 * item + j; return bh < n_bh ? bh : 2 * item; };
+  auto issue_qk = [&](int item) {                    // one thread
+    mbar_arrive_expect_tx(&bars[0], 16384u + (uint32_t)n_keys * 128u);
+    for (int j = 0; j < 2; ++j) {
+      const int bh = bh_of(item, j), b = bh / a.nh, h = bh - b * a.nh;
+      tma_load_2d(sQ + j * 8192, &tmKV, &bars[0], h * 64, b * a.L);
+      uint8_t* k = sK + j * KR * 128;
+      for (int r = 0; r < a.P8; r += 8) tma_load_2d(k + r * 128, &tmKp, &bars[0], 0, bh * a.P + r);
+      tma_load_2d(k + a.P8 * 128, &tmKV, &bars[0], H + h * 64, b * a.L);
+    }
+  };
+  auto issue_v = [&](int item) {                     // one thread
+    mbar_arrive_expect_tx(&bars[3], (uint32_t)n_keys * 128u);
+    for (int j = 0; j < 2; ++j) {
+      const int bh = bh_of(item, j), b = bh / a.nh, h = bh - b * a.nh;
+      uint8_t* v = sV + j * KR * 128;
+      for (int r = 0; r < a.P8; r += 8) tma_load_2d(v + r * 128, &tmVp, &bars[3], 0, bh * a.P + r);
+      tma_load_2d(v + a.P8 * 128, &tmKV, &bars[3], 2 * H + h * 64, b * a.L);
+    }
+  };
+  if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
+
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  const float sc2 = a.scale * kFwdLog2e;
+  const int row8 = row & 7;
+  const uint32_t prow_off = (row >> 3) * 1024 + row8 * 128;
+  const int units = KR >> 3;                         // per item
+  const int u0 = blk * units;                        // first unit (8 S columns) of this row's item
+  const uint32_t aMask = smem_u32(sMask), aPs = smem_u32(sP), aExch = smem_u32(sExch);
+
+  // S column `c` of the pair -> additive mask (x log2 e); 2 KR <= 192 < kFwdThreadsSmall
+  auto fetch_mask = [&](int item, int c) -> float {
+    if (c >= n_keys) return 0.f;
+    const int j = c >= KR ? 1 : 0, k = c - j * KR;
+    if (k < a.P8) return (k < a.P) ? 0.f : -INFINITY;
+    const int t = k - a.P8;
+    if (t >= a.L) return -INFINITY;
+    const int b = bh_of(item, j) / a.nh;
+    return a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kFwdLog2e;
+  };
+  float mask_next = (int)blockIdx.x < n_items ? fetch_mask(blockIdx.x, tid) : 0.f;
+
+  uint32_t ph = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ph ^= 1) {
+    const int bh = 2 * item + blk;
+    const bool exists = bh < n_bh;
+    const int b = bh / a.nh, h = bh - b * a.nh;
+    const int q = row & 63;
+    if (tid < n_keys) sMask[tid] = mask_next;
+    if (item + (int)gridDim.x < n_items) mask_next = fetch_mask(item + gridDim.x, tid);
+    if (tid == 0) {
+      mbar_wait(&bars[0], ph);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+      const uint32_t idesc = make_idesc_bf16(128, n_keys, false, false);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16_ss(tmem_base, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                    idesc, k > 0 ? 1u : 0u);
+      umma_commit(&bars[1]);
+    }
+    __syncthreads();
+    mbar_wait(&bars[1], ph);
+    __syncwarp();
+    tc_fence_after();
+    if (tid == 0 && item + (int)gridDim.x < n_items) issue_qk(item + gridDim.x);
+    __syncwarp();
+
+    float mx = -INFINITY;
+    for (int u = half; u < units; u += 2) {
+      const int c = (u0 + u) << 3;
+      uint32_t r[8];
+      tmem_ld_32x32b_x8(t_row + c, r);
+      const float4 m0 = lds_f4(aMask + c * 4);
+      const float4 m1 = lds_f4(aMask + c * 4 + 16);
+      tmem_ld_wait();
+      mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[0]), sc2, m0.x), fmaf(__uint_as_float(r[1]), sc2, m0.y)),
+                           fmaxf(fmaf(__uint_as_float(r[2]), sc2, m0.z), fmaf(__uint_as_float(r[3]), sc2, m0.w))));
+      mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[4]), sc2, m1.x), fmaf(__uint_as_float(r[5]), sc2, m1.y)),
+                           fmaxf(fmaf(__uint_as_float(r[6]), sc2, m1.z), fmaf(__uint_as_float(r[7]), sc2, m1.w))));
+    }
+    sts_f32(aExch + (half * 128 + row) * 4, mx);
+    __syncthreads();
+    const float mx2 = fmaxf(lds_f32(aExch + row * 4), lds_f32(aExch + (128 + row) * 4));
+
+    const uint32_t rowkey =
+        a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
+    const float mxs = a.drop_thr ? mx2 - log2f(a.drop_scale) : mx2;
+    float sum = 0.f;
+    for (int u = half; u < units; u += 2) {
+      const int cl = u << 3, c = (u0 + u) << 3;
+      uint32_t r[8];
+      tmem_ld_32x32b_x8(t_row + c, r);
+      const float4 m0 = lds_f4(aMask + c * 4);
+      const float4 m1 = lds_f4(aMask + c * 4 + 16);
+      const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      tmem_ld_wait();
+      float p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sc2, mk[j] - mxs));
+        sum += p[j];
+      }
+      if (a.drop_thr) attn_drop_apply8(rowkey, cl < a.P8 ? cl : a.kbase + (cl - a.P8), a.drop_thr, p);
+      uint4 w;
+      w.x = pack_bf16x2(p[0], p[1]); w.y = pack_bf16x2(p[2], p[3]);
+      w.z = pack_bf16x2(p[4], p[5]); w.w = pack_bf16x2(p[6], p[7]);
+      const int ug = u0 + u;
+      sts_u4(aPs + (ug >> 3) * 16384 + prow_off + (((ug & 7) ^ row8) << 4), w);
+    }
+    sts_f32(aExch + (256 + half * 128 + row) * 4, sum);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (tid == 0) {
+      mbar_wait(&bars[3], ph);
+      tc_fence_after();
+      const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
+      const int ksteps = n_keys / 16;
+      for (int j = 0; j < ksteps; ++j)
+        umma_f16_ss(tmem_base + S_COLS, make_smem_desc_sw128(aP + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(aV + j * 2048, 8192, 1024), idesc, j > 0 ? 1u : 0u);
+      umma_commit(&bars[2]);
+    }
+    __syncwarp();
+    const float total = lds_f32(aExch + (256 + row) * 4) + lds_f32(aExch + (384 + row) * 4);
+    mbar_wait(&bars[2], ph);
+    __syncwarp();
+    tc_fence_after();
+    if (tid == 0 && item + (int)gridDim.x < n_items) issue_v(item + gridDim.x);
+    __syncwarp();
+
+    const float inv = a.drop_scale / total;
+    const bool valid = exists && q < a.L;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + S_COLS + half * 32, r);
+    tmem_ld_wait();
+    if (valid) {
+      uint4* o = reinterpret_cast<uint4*>(ctx + ((long long)b * a.L + q) * ld_ctx + h * 64 + half * 32);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) * inv, __uint_as_float(r[v * 8 + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]) * inv, __uint_as_float(r[v * 8 + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]) * inv, __uint_as_float(r[v * 8 + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]) * inv, __uint_as_float(r[v * 8 + 7]) * inv);
+        o[v] = w;
+      }
+      if (half == 0) lse_out[((long long)b * a.nh + h) * a.L + q] = (mxs + log2f(total)) * 0.6931471805599453f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+static size_t attn_fwd_tc_pair_smem(const AttnTcArgs& a) {
+  const int n_keys = 2 * (a.P8 + 64);
+  const int n_chunks = (n_keys + 63) / 64;
+  return 1024 + 16384 + 2 * (size_t)n_keys * 128 + (size_t)n_chunks * 16384 + ((n_keys + 15) / 16) * 64 + 2048 + 64;
+}
+
+// two items per tile pay when a tile would otherwise be half empty and two CTAs still fit an SM
+static bool attn_fwd_tc_pair_ok(const AttnTcArgs& a) {
+  static const char* env = getenv("MTVAF_ATTN_FWD_PAIR");                  // experiment knob: 0 = off
+  if (env && atoi(env) == 0) return false;
+  return a.L <= 64 && a.kt0 == 0 && a.Lk == a.L && 2 * (a.P8 + 64) <= 192 && a.B * a.nh >= 2 &&
+         2 * attn_fwd_tc_pair_smem(a) <= 227 * 1024;
+}
+
 size_t attn_fwd_tc_smem(const AttnTcArgs& a) {
   const int key_rows = a.P8 + a.L64;
   const int n_chunks = (a.N16 + 63) / 64;
@@ -289,7 +517,18 @@ int attn_fwd_tc_launch(const AttnTcArgs& a, const AttnTcMaps& m, void* ctx, int6
   const size_t smem = attn_fwd_tc_smem(a);
   const int n_items = a.B * a.nh * ((a.L + 127) / 128);
   const bool big = a.N16 > 192;
-  static bool set0 = false, set1 = false;
+  static bool set0 = false, set1 = false, set2 = false;
+  if (attn_fwd_tc_pair_ok(a)) {
+    if (!set2) {
+      MTVAF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set2 = true;
+    }
+    const int n_pairs = (a.B * a.nh + 1) / 2;
+    const int grid = n_pairs < 2 * sm_count() ? n_pairs : 2 * sm_count();
+    attn_fwd_tc_pair_kernel<<<grid, kFwdThreadsSmall, attn_fwd_tc_pair_smem(a), st>>>(m.kv, m.kp, m.vp, a, (__nv_bfloat16*)ctx, ld_ctx, lse);
+    MTVAF_LAUNCH_CHECK();
+    return 0;
+  }
   if (!big) {
     if (!set0) {
       MTVAF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

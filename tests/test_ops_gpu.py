@@ -518,6 +518,36 @@ def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
             assert rel_err(a, b) < 2e-2, (impl, nm)
 
 
+@pytest.mark.parametrize("B,Lq,P,nh,p_drop", [(1, 64, 16, 3, 0.0), (3, 64, 16, 3, 0.1), (5, 33, 0, 1, 0.1), (2, 64, 32, 12, 0.1),
+                                               (7, 9, 3, 5, 0.0)])
+def test_attention_fwd_two_items_per_tile(ops, B, Lq, P, nh, p_drop):
+    """L <= 64 runs two (batch, head) items per 128-row tile (attn_fwd_tc_pair_kernel): odd item counts (the last pair is
+    half empty), pairs that straddle two batch rows (odd head count), ragged masks -- against the SIMT kernel (same
+    dropout hash) and, without dropout, the fp32 reference."""
+    d = 64
+    bf = torch.bfloat16
+    qkv = rnd(B * Lq, 3 * nh * d, seed=21, dtype=bf)
+    kp = rnd(B, nh, P, d, seed=22, dtype=bf) if P else None
+    vp = rnd(B, nh, P, d, seed=23, dtype=bf) if P else None
+    g = torch.Generator().manual_seed(6)
+    lens = torch.randint(1, Lq + 1, (B,), generator=g)
+    mask = (torch.arange(Lq)[None] < lens[:, None]).long().to(DEV)
+    res = {}
+    try:
+        for impl in ("simt", "auto"):
+            ops.set_attention_impl(impl)
+            res[impl] = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p_drop, seed=7)[:2]
+    finally:
+        ops.set_attention_impl("auto")
+    for a, b in zip(res["auto"], res["simt"]):
+        assert torch.isfinite(a.float()).all()
+        assert rel_err(a, b) < 2e-2
+    if p_drop == 0.0:
+        ref, _ = _attn_ref(qkv.float().cpu(), None if kp is None else kp.float().cpu(), None if vp is None else vp.float().cpu(),
+                           mask.cpu(), B, Lq, nh, d)
+        assert rel_err(res["auto"][0], ref.to(DEV)) < 2e-2
+
+
 # ---------------------------------------------------------------------------------------- fusion
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gate_and_mean4(ops, dtype):
