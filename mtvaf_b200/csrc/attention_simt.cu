@@ -569,6 +569,8 @@ extern "C" int mtvaf_attention_bwd_ex(const void* dctx, int64_t ld_dctx, const v
     AttnTcMaps tm;
     bool ok = false;
     if (int rc = attn_tc_prepare(qkv, ld_qkv, kp, vp, P, key_mask, B, L, nh, p_drop, seed, &ta, &tm, &ok)) return rc;
+    if (ok && attention_impl_override() == 0 && attn_bwd_pair_supported(ta))
+      return attn_bwd_pair_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, d_bias_qkv, st);
     if (ok && attention_impl_override() == 0 && attn_bwd_pipe_supported(ta))
       return attn_bwd_pipe_launch(ta, tm, dctx, ld_dctx, ctx, ld_ctx, lse, dqkv, ld_dqkv, dkp, dvp, d_bias_qkv, st);
     if (ok && attn_bwd_tc_supported(ta)) {

@@ -47,6 +47,11 @@ bool attn_bwd_pipe_supported(const AttnTcArgs& a);
 int attn_bwd_pipe_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
                          int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
                          float* dbias, cudaStream_t st);
+// short text (L <= 64, P <= 16): two (batch, head) items per tile, attention_tc_bwd_pair.cu
+bool attn_bwd_pair_supported(const AttnTcArgs& a);
+int attn_bwd_pair_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,
+                         int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, float* dkp, float* dvp,
+                         float* dbias, cudaStream_t st);
 // long-text backward (128 < L <= 512), attention_tc_bwd_long.cu
 bool attn_bwd_long_supported(const AttnTcArgs& a);
 int attn_bwd_long_launch(const AttnTcArgs& a, const AttnTcMaps& m, const void* dctx, int64_t ld_dctx, const void* ctx,

@@ -384,7 +384,7 @@ def test_attention_fwd_bwd(ops, dtype, B, Lq, P):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,Lq,P", [(3, 128, 16), (2, 100, 16), (3, 40, 36), (1, 200, 100)])
+@pytest.mark.parametrize("B,Lq,P", [(3, 128, 16), (2, 100, 16), (3, 40, 36), (1, 200, 100), (3, 64, 16), (3, 37, 5)])
 def test_attention_bwd_qkv_bias_grad(ops, dtype, B, Lq, P):
     """mtvaf_attention_bwd_ex: d_bias += column sums of dqkv on every kernel path (pipelined tcgen05 drain warps for
     L <= 128 / P <= 16, generic tcgen05 + colsum, SIMT + colsum), accumulating into what is already there."""
@@ -520,10 +520,10 @@ def test_attention_tc_matches_simt(ops, B, Lq, P, p_drop):
 
 @pytest.mark.parametrize("B,Lq,P,nh,p_drop", [(1, 64, 16, 3, 0.0), (3, 64, 16, 3, 0.1), (5, 33, 0, 1, 0.1), (2, 64, 32, 12, 0.1),
                                                (7, 9, 3, 5, 0.0)])
-def test_attention_fwd_two_items_per_tile(ops, B, Lq, P, nh, p_drop):
-    """L <= 64 runs two (batch, head) items per 128-row tile (attn_fwd_tc_pair_kernel): odd item counts (the last pair is
-    half empty), pairs that straddle two batch rows (odd head count), ragged masks -- against the SIMT kernel (same
-    dropout hash) and, without dropout, the fp32 reference."""
+def test_attention_two_items_per_tile(ops, B, Lq, P, nh, p_drop):
+    """L <= 64 runs two (batch, head) items per 128-row tile (attn_fwd_tc_pair_kernel; attn_bwd_pair_kernel for P <= 16):
+    odd item counts (the last pair is half empty), pairs that straddle two batch rows (odd head count), ragged masks --
+    forward and backward against the SIMT kernels (same dropout hash) and, without dropout, the fp32 reference."""
     d = 64
     bf = torch.bfloat16
     qkv = rnd(B * Lq, 3 * nh * d, seed=21, dtype=bf)
@@ -532,16 +532,23 @@ def test_attention_fwd_two_items_per_tile(ops, B, Lq, P, nh, p_drop):
     g = torch.Generator().manual_seed(6)
     lens = torch.randint(1, Lq + 1, (B,), generator=g)
     mask = (torch.arange(Lq)[None] < lens[:, None]).long().to(DEV)
+    dctx = rnd(B * Lq, nh * d, seed=24, dtype=bf)
     res = {}
     try:
         for impl in ("simt", "auto"):
             ops.set_attention_impl(impl)
-            res[impl] = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p_drop, seed=7)[:2]
+            ctx, lse, _ = ops.attention_fwd(qkv, kp, vp, mask, B, Lq, nh, d, p_drop=p_drop, seed=7)
+            dkp = torch.zeros(B, nh, P, d, device=DEV) if P else None
+            dvp = torch.zeros(B, nh, P, d, device=DEV) if P else None
+            dqkv = ops.attention_bwd(dctx, qkv, kp, vp, mask, ctx, lse, B, Lq, nh, d, dkp, dvp, p_drop=p_drop, seed=7)
+            res[impl] = (ctx, lse, dqkv, dkp, dvp)
     finally:
         ops.set_attention_impl("auto")
-    for a, b in zip(res["auto"], res["simt"]):
-        assert torch.isfinite(a.float()).all()
-        assert rel_err(a, b) < 2e-2
+    for nm, a, b in zip(("ctx", "lse", "dqkv", "dkp", "dvp"), res["auto"], res["simt"]):
+        if a is None:
+            continue
+        assert torch.isfinite(a.float()).all(), nm
+        assert rel_err(a, b) < 2e-2, nm
     if p_drop == 0.0:
         ref, _ = _attn_ref(qkv.float().cpu(), None if kp is None else kp.float().cpu(), None if vp is None else vp.float().cpu(),
                            mask.cpu(), B, Lq, nh, d)
