@@ -103,33 +103,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int units = a.N16 >> 3;
   const uint32_t aMask = smem_u32(sMask), aPs = smem_u32(sP), aExch = smem_u32(sExch);   // explicit shared-space accesses
 
-  // key `k` of batch row `b` -> additive mask; keys >= N16 are never read (N16 <= 448 < kFwdThreads)
-  auto fetch_mask = [&](int b, int k) -> float {
+  // key `k` -> additive mask (x log2 e); keys >= N16 are never read (N16 <= 448 < 2 * kFwdThreads).  Only text keys inside
+  // the window depend on memory: the raw key-mask word is PREFETCHED one item ahead and nothing is computed from it until
+  // the next item stores the mask, so the load has a whole item to land (computing the value right after the load stalled
+  // every warp on the long scoreboard once per item)
+  auto key_const = [&](int k) -> float {
     if (k >= a.N16) return 0.f;
     if (k < a.P8) return (k < a.P) ? 0.f : -INFINITY;
-    const int t = k - a.P8;
-    return (t < a.Lk) ? (a.key_mask[(long long)b * a.L + a.kt0 + t] != 0 ? 0.f : -10000.0f * kFwdLog2e) : -INFINITY;
+    return -INFINITY;                                  // text key outside the window (inside: from the key mask)
   };
-  float mask_next[2] = {0.f, 0.f};                   // (N16 <= 448 < 2 * kFwdThreads)
+  const bool dyn0 = tid >= a.P8 && tid < a.N16 && tid - a.P8 < a.Lk;
+  const bool dyn1 = tid + kFwdThreads >= a.P8 && tid + kFwdThreads < a.N16 && tid + kFwdThreads - a.P8 < a.Lk;
+  const float const0 = key_const(tid), const1 = key_const(tid + kFwdThreads);
+  auto fetch_raw = [&](int b, bool dyn, int k) -> long long {
+    return dyn ? __ldg(a.key_mask + (long long)b * a.L + a.kt0 + (k - a.P8)) : 1;
+  };
+  long long km_next[2] = {1, 1};
   if ((int)blockIdx.x < n_items) {
     const int b0 = (int)blockIdx.x / q_tiles / a.nh;
-    mask_next[0] = fetch_mask(b0, tid);
-    mask_next[1] = fetch_mask(b0, tid + kFwdThreads);
+    km_next[0] = fetch_raw(b0, dyn0, tid);
+    km_next[1] = fetch_raw(b0, dyn1, tid + kFwdThreads);
   }
+  const unsigned long long seed_eff = a.drop_thr ? step_seed(a.seed, a.step) : 0ull;
 
   uint32_t ph = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ph ^= 1) {
     const int qt = item % q_tiles, bh = item / q_tiles;
     const int b = bh / a.nh, h = bh - b * a.nh;
     const int q = qt * 128 + row;
-    // additive key mask (x log2 e) in smem-key numbering: prefix rows [0,P) visible, [P,P8) padding, text rows follow.
-    // The values were fetched one item ahead (mask_next): the global load no longer sits in front of the barrier.
-    if (tid < a.N16) sMask[tid] = mask_next[0];
-    if (tid + kFwdThreads < a.N16) sMask[tid + kFwdThreads] = mask_next[1];
+    // additive key mask (x log2 e) in smem-key numbering: prefix rows [0,P) visible, [P,P8) padding, text rows follow
+    if (tid < a.N16) sMask[tid] = dyn0 ? (km_next[0] != 0 ? 0.f : -10000.0f * kFwdLog2e) : const0;
+    if (tid + kFwdThreads < a.N16) sMask[tid + kFwdThreads] = dyn1 ? (km_next[1] != 0 ? 0.f : -10000.0f * kFwdLog2e) : const1;
     if (item + (int)gridDim.x < n_items) {
       const int bn = (item + (int)gridDim.x) / q_tiles / a.nh;
-      mask_next[0] = fetch_mask(bn, tid);
-      mask_next[1] = fetch_mask(bn, tid + kFwdThreads);
+      km_next[0] = fetch_raw(bn, dyn0, tid);
+      km_next[1] = fetch_raw(bn, dyn1, tid + kFwdThreads);
     }
     if (tid == 0) {
       mbar_wait(&bars[0], ph);
@@ -176,7 +184,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ---- pass 2: P = exp2(x - max), row sum, dropout, bf16 P -> shared memory.  With dropout the 1/(1-p) scale
     // rides in the exponent (max - log2(scale)): P is born scaled, the row sum is corrected once at the end.
     const uint32_t rowkey =
-        a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
+        a.drop_thr ? attn_drop_rowkey(seed_eff, ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
     const float mxs = a.drop_thr ? mx2 - log2f(a.drop_scale) : mx2;
     float sum = 0.f;
     for (int u = half; u < units; u += NPART) {
@@ -359,17 +367,16 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
   const int u0 = blk * units;                        // first unit (8 S columns) of this row's item
   const uint32_t aMask = smem_u32(sMask), aPs = smem_u32(sP), aExch = smem_u32(sExch);
 
-  // S column `c` of the pair -> additive mask (x log2 e); 2 KR <= 192 < kFwdThreadsSmall
-  auto fetch_mask = [&](int item, int c) -> float {
-    if (c >= n_keys) return 0.f;
-    const int j = c >= KR ? 1 : 0, k = c - j * KR;
-    if (k < a.P8) return (k < a.P) ? 0.f : -INFINITY;
-    const int t = k - a.P8;
-    if (t >= a.L) return -INFINITY;
-    const int b = bh_of(item, j) / a.nh;
-    return a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kFwdLog2e;
+  // S column c = tid of the pair -> additive mask (x log2 e); 2 KR <= 192 < kFwdThreadsSmall.  The raw key-mask word is
+  // prefetched one item ahead and only turned into a value when the next item stores it (see the kernel above)
+  const int mj = tid >= KR ? 1 : 0, mk_ = tid - mj * KR;               // item of the pair / key within it
+  const bool m_dyn = tid < n_keys && mk_ >= a.P8 && mk_ - a.P8 < a.L;
+  const float m_const = tid >= n_keys ? 0.f : (mk_ < a.P8 ? (mk_ < a.P ? 0.f : -INFINITY) : -INFINITY);
+  auto fetch_raw = [&](int item) -> long long {
+    return m_dyn ? __ldg(a.key_mask + (long long)(bh_of(item, mj) / a.nh) * a.L + (mk_ - a.P8)) : 1;
   };
-  float mask_next = (int)blockIdx.x < n_items ? fetch_mask(blockIdx.x, tid) : 0.f;
+  long long km_next = (int)blockIdx.x < n_items ? fetch_raw(blockIdx.x) : 1;
+  const unsigned long long seed_eff = a.drop_thr ? step_seed(a.seed, a.step) : 0ull;
 
   uint32_t ph = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ph ^= 1) {
@@ -377,8 +384,8 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
     const bool exists = bh < n_bh;
     const int b = bh / a.nh, h = bh - b * a.nh;
     const int q = row & 63;
-    if (tid < n_keys) sMask[tid] = mask_next;
-    if (item + (int)gridDim.x < n_items) mask_next = fetch_mask(item + gridDim.x, tid);
+    if (tid < n_keys) sMask[tid] = m_dyn ? (km_next != 0 ? 0.f : -10000.0f * kFwdLog2e) : m_const;
+    if (item + (int)gridDim.x < n_items) km_next = fetch_raw(item + gridDim.x);
     if (tid == 0) {
       mbar_wait(&bars[0], ph);
       tc_fence_after();
@@ -415,7 +422,7 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
     const float mx2 = fmaxf(lds_f32(aExch + row * 4), lds_f32(aExch + (128 + row) * 4));
 
     const uint32_t rowkey =
-        a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
+        a.drop_thr ? attn_drop_rowkey(seed_eff, ((unsigned long long)b * a.nh + h) * a.L + q) : 0u;
     const float mxs = a.drop_thr ? mx2 - log2f(a.drop_scale) : mx2;
     float sum = 0.f;
     for (int u = half; u < units; u += 2) {

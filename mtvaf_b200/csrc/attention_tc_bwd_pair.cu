@@ -85,7 +85,8 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
   uint64_t* bar_o = bars + 8;     //     gradients drained           (4 drain-warp arrivals)
   uint64_t* bar_d = bars + 9;     // [2] D_q of the item in this buffer is in smem (4 drain-warp arrivals)
   uint64_t* bar_x = bars + 11;    //     prefix gradients (aliasing S) drained (2 drain-warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_gx = bars + 12;   //     transposed prefix gradients in TMEM (tcgen05.commit, ahead of bar_g)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = a.nh * 64;
@@ -107,6 +108,7 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
     mbar_init(&bar_d[0], kDrainWarps);
     mbar_init(&bar_d[1], kDrainWarps);
     mbar_init(bar_x, 2);
+    mbar_init(bar_gx, 1);
     fence_barrier_init();
   }
   __syncwarp();
@@ -129,10 +131,12 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
         uint8_t* k = sK0 + buf * lay.k_stride;
         mbar_arrive_expect_tx(&bar_qk[buf], 16384u + kv_bytes);
         mbar_arrive_expect_tx(&bar_do[buf], 16384u);
+#pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const int bh = bh_of(item, j), b = bh / a.nh, h = bh - b * a.nh;
           tma_load_2d(q + j * 8192, &tmKV, &bar_qk[buf], h * 64, b * a.L);
           tma_load_2d(k + j * 8192, &tmKV, &bar_qk[buf], H + h * 64, b * a.L);
+#pragma unroll 1
           for (int r = 0; r < a.P8; r += 8)
             tma_load_2d(k + (NT + j * a.P8 + r) * 128, &tmKp, &bar_qk[buf], 0, bh * a.P + r);
           tma_load_2d(sdO0 + buf * 16384 + j * 8192, &tmdO, &bar_do[buf], h * 64, b * a.L);
@@ -140,14 +144,18 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
       };
       auto load_v = [&](int item) {
         mbar_arrive_expect_tx(bar_v, kv_bytes);
+#pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const int bh = bh_of(item, j), b = bh / a.nh, h = bh - b * a.nh;
           tma_load_2d(sV + j * 8192, &tmKV, bar_v, 2 * H + h * 64, b * a.L);
+#pragma unroll 1
           for (int r = 0; r < a.P8; r += 8)
             tma_load_2d(sV + (NT + j * a.P8 + r) * 128, &tmVp, bar_v, 0, bh * a.P + r);
         }
       };
-      if (first < n_items) { load_qkdo(first, 0); load_v(first); }
+      // ONE copy of everything this thread executes, as rolled loops: it runs alone, once per item, through code that the
+      // other 20 warps' loops have long evicted from the 32 KB instruction cache -- with the loads and MMAs unrolled
+      // (34 KB of code for this one thread) every 128-byte line of it was an L2 round trip (~85 cycles per MMA issued)
       const uint32_t idesc_s = make_idesc_bf16(128, NS, false, false);
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);
       const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
@@ -168,65 +176,68 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
       const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), 16384, 1024);
       const uint64_t P_mn = make_smem_desc_sw128(smem_u32(sP), 16384, 1024);
       const int ksteps = NS / 16;
-      int il = 0;
-      for (int item = first; item < n_items; item += gridDim.x, ++il) {
+      int il = -1;                                       // iteration -1 = prologue: only the first item's loads
+#pragma unroll 1
+      for (int item = first - (int)gridDim.x; item < n_items; item += gridDim.x, ++il) {
+        const int next = item + gridDim.x;
+        const bool live = il >= 0;
         const int buf = il & 1;
         const uint32_t ph = il & 1, ph2 = (il >> 1) & 1;
-        const int next = item + gridDim.x;
         const uint64_t q_k = q_k0 + buf * q_step, k_k = k_k0 + buf * k_step, o_k = o_k0 + buf * q_step;
         const uint64_t k_mn = k_mn0 + buf * k_step, q_mn = q_mn0 + buf * q_step, o_mn = o_mn0 + buf * q_step;
-        // ---- S = Q K^T, dP = dO V^T   (the S / dP columns are free: bar_p of the previous item was awaited
-        //      before that item's gradient MMAs were issued -- except the S columns the previous item's transposed
-        //      prefix gradients landed in: the drain warps release those first)
-        mbar_wait(&bar_qk[buf], ph2);
-        if (il > 0 && a.P8 > 0) mbar_wait(bar_x, ph ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + TC_S, q_k + k * 2, k_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
-        mbar_wait(&bar_do[buf], ph2);
-        mbar_wait(bar_v, ph);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + TC_DP, o_k + k * 2, dV_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
-        // ---- the other Q / K / dO buffers were last read by the previous item's gradient MMAs
-        if (il > 0) mbar_wait(bar_g, ph ^ 1);
-        if (next < n_items) load_qkdo(next, buf ^ 1);
-        mbar_wait(bar_s, ph);                           // dP retired: V is free
+        if (live) {
+          // ---- S = Q K^T, dP = dO V^T   (the S / dP columns are free: bar_p of the previous item was awaited
+          //      before that item's gradient MMAs were issued -- except the S columns the previous item's transposed
+          //      prefix gradients landed in: the drain warps release those first)
+          mbar_wait(&bar_qk[buf], ph2);
+          if (il > 0 && a.P8 > 0) mbar_wait(bar_x, ph ^ 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + TC_S, q_k + k * 2, k_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          mbar_wait(&bar_do[buf], ph2);
+          mbar_wait(bar_v, ph);
+          tc_fence_after();
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + TC_DP, o_k + k * 2, dV_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_s);
+          // ---- the other Q / K / dO buffers were last read by the previous item's gradient MMAs
+          if (il > 0) mbar_wait(bar_g, ph ^ 1);
+        }
+        if (next < n_items) load_qkdo(next, (il + 1) & 1);
+        if (live) mbar_wait(bar_s, ph);                  // dP retired: V is free
         if (next < n_items) load_v(next);
+        if (!live) continue;
         // ---- gradients: need P / dS of this item and the previous item's gradients drained from TMEM
         mbar_wait(bar_p, ph);
         if (il > 0) mbar_wait(bar_o, ph ^ 1);
         tc_fence_after();
-        // dQ[q, d] = sum_key dS[q, key] K[key, d]   (K-major dS: 64-key chunks of 16 KB, 32 B per 16-key step)
-#pragma unroll
-        for (int j = 0; j < 10; ++j)
-          if (j < ksteps)
-            umma_f16_ss(tmem_base + TC_DQ, dS_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + j * 128, idesc_q,
-                        j > 0 ? 1u : 0u);
-        // text keys: dK[key, d] = sum_q dS[q, key] Q[q, d] ; dV[key, d] = sum_q P[q, key] dO[q, d]
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_f16_ss(tmem_base + TC_DK, dS_mn + j * 128, q_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_f16_ss(tmem_base + TC_DV, P_mn + j * 128, o_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
         if (a.P8 > 0) {
-          // prefix keys, transposed: dK_p^T[d, key] = sum_q Q[q, d] dS[q, key] ; dV_p^T[d, key] = sum_q dO[q, d] P[q, key]
+          // prefix keys FIRST (the next S MMA waits for their drain, which then runs under the text gradients), transposed:
+          // dK_p^T[d, key] = sum_q Q[q, d] dS[q, key] ; dV_p^T[d, key] = sum_q dO[q, d] P[q, key]
           // (A = Q / dO as MN-major operands: rows 64..127 of the M = 128 tile read past the 64 real columns,
           //  finite or not: their output lanes are never stored).  These land in the S columns: P / dS are written
           //  (bar_p), so S is dead.
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < 8; ++j)
-            umma_f16_ss(tmem_base + TC_DKP, q_mn + j * 128, dS_mn + cp * 1024 + j * 128, idesc_p,
-                        j > 0 ? 1u : 0u);
-#pragma unroll
+            umma_f16_ss(tmem_base + TC_DKP, q_mn + j * 128, dS_mn + cp * 1024 + j * 128, idesc_p, j > 0 ? 1u : 0u);
+#pragma unroll 1
           for (int j = 0; j < 8; ++j)
-            umma_f16_ss(tmem_base + TC_DVP, o_mn + j * 128, P_mn + cp * 1024 + j * 128, idesc_p,
-                        j > 0 ? 1u : 0u);
+            umma_f16_ss(tmem_base + TC_DVP, o_mn + j * 128, P_mn + cp * 1024 + j * 128, idesc_p, j > 0 ? 1u : 0u);
+          umma_commit(bar_gx);
         }
+        // dQ[q, d] = sum_key dS[q, key] K[key, d]   (K-major dS: 64-key chunks of 16 KB, 32 B per 16-key step)
+#pragma unroll 1
+        for (int j = 0; j < ksteps; ++j)
+          umma_f16_ss(tmem_base + TC_DQ, dS_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + j * 128, idesc_q, j > 0 ? 1u : 0u);
+        // text keys: dK[key, d] = sum_q dS[q, key] Q[q, d] ; dV[key, d] = sum_q P[q, key] dO[q, d]
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j)
+          umma_f16_ss(tmem_base + TC_DK, dS_mn + j * 128, q_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j)
+          umma_f16_ss(tmem_base + TC_DV, P_mn + j * 128, o_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
         umma_commit(bar_g);
       }
     }
@@ -282,11 +293,11 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
       const bool row_ok = row_in && bh < n_bh;
       // the next item's D while the softmax warps work on this one (its buffer was last read two items ago)
       if (item + (int)gridDim.x < n_items) compute_d(item + gridDim.x, (il + 1) & 1, ((il + 1) >> 1) & 1);
-      mbar_wait(bar_g, il & 1);                        // this item's gradient MMAs have retired
-      tc_fence_after();
       // prefix rows FIRST (they sit in the S columns the next item's S MMA is waiting for), transposed accumulators:
       // lane = head-dim index d (TMEM lanes 0..63), column = prefix key of item a [0, P8) | item b [P8, 2 P8)
       if (a.P8 > 0 && quad < 2) {                        // warp-uniform
+        mbar_wait(bar_gx, il & 1);                       // committed ahead of the text gradients
+        tc_fence_after();
         uint32_t rk[32], rv[32];
         tmem_ld_32x32b_x32(t_row + TC_DKP, rk);
         tmem_ld_32x32b_x32(t_row + TC_DVP, rv);
@@ -311,12 +322,15 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
           }
         }
       }
+      mbar_wait(bar_g, il & 1);                        // this item's gradient MMAs have retired
+      tc_fence_after();
       // dQ | dK | dV of the text rows: lane = row, 64 head-dim columns each = one full 128-byte line per lane
-#pragma unroll
+      // (rolled: one copy of the store + bias-gradient code instead of six keeps the kernel inside the instruction cache)
+#pragma unroll 1
       for (int which = 0; which < 3; ++which) {
-        const int tc = which == 0 ? TC_DQ : (which == 1 ? TC_DK : TC_DV);
+        const int tc = TC_DQ + which * 64;
         __nv_bfloat16* dst = dqkv + ((long long)b * a.L + qrow) * ld_dqkv + which * H + h * 64;
-#pragma unroll
+#pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + tc + hf * 32, r);
@@ -371,25 +385,30 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
     const int units = 8 + (a.P8 >> 3);                 // per row: 8 text units + the item's prefix units
     const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
 
-    // key column c: text row (c & 63) of item (c >> 6) for c < 128, then the prefix rows of item a, item b
-    auto fetch_mask = [&](int item) -> float {
-      if (tid >= NS) return 0.f;
-      if (tid < NT) {
-        const int t = tid & 63, b = bh_of(item, tid >> 6) / a.nh;
-        return (t < a.L) ? (a.key_mask[(long long)b * a.L + t] != 0 ? 0.f : -10000.0f * kLog2ePair) : -INFINITY;
-      }
-      const int k = tid - NT;
-      return ((k >= a.P8 ? k - a.P8 : k) < a.P) ? 0.f : -INFINITY;
+    // key column c = tid: text row (c & 63) of item (c >> 6) for c < 128, then the prefix rows of item a, item b.
+    // Only text columns inside the sequence depend on memory; what is PREFETCHED one item ahead is the raw key-mask word
+    // and the raw log-sum-exp: nothing is computed from them until the next item uses them, so the loads have a whole
+    // item to land (computing the mask value right after the load stalled every softmax warp on the long scoreboard once
+    // per item -- 25 % of this kernel's stall samples, profiles/r2_ncu_attn_bwd_pair.md).
+    const bool m_dyn = tid < NT && (tid & 63) < a.L;
+    const float m_const = tid >= NS ? 0.f
+                        : (tid < NT ? -INFINITY : (((tid - NT >= a.P8) ? tid - NT - a.P8 : tid - NT) < a.P ? 0.f : -INFINITY));
+    auto fetch_mask_raw = [&](int item) -> long long {
+      if (!m_dyn) return 1;
+      const int b = bh_of(item, tid >> 6) / a.nh;
+      return __ldg(a.key_mask + (long long)b * a.L + (tid & 63));
     };
-    auto fetch_lse = [&](int item) -> float {
+    auto fetch_lse_raw = [&](int item) -> float {
       const int bh = 2 * item + blk;
-      return (row_in && bh < n_bh) ? lse[(long long)bh * a.L + qrow] * kLog2ePair - log2_ds : INFINITY;
+      return (row_in && bh < n_bh) ? __ldg(lse + (long long)bh * a.L + qrow) : 0.f;
     };
+    const unsigned long long seed_eff = a.drop_thr ? step_seed(a.seed, a.step) : 0ull;
 
-    float m_next = 0.f, lse_next = 0.f;
+    long long km_next = 1;
+    float lse_next = 0.f;
     if (first < n_items) {
-      m_next = fetch_mask(first);
-      lse_next = fetch_lse(first);
+      km_next = fetch_mask_raw(first);
+      lse_next = fetch_lse_raw(first);
     }
     int il = 0;
     int prev = -1;
@@ -400,11 +419,11 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
       const int next = item + gridDim.x;
       float* sMask = sMask0 + buf * 160;
       // ---- this item's prefetched scalars; the next item's travel while this one is processed
-      if (tid < NS) sMask[tid] = m_next;
-      const float lse2 = lse_next;
+      if (tid < NS) sMask[tid] = m_dyn ? (km_next != 0 ? 0.f : -10000.0f * kLog2ePair) : m_const;
+      const float lse2 = (row_in && bh < n_bh) ? lse_next * kLog2ePair - log2_ds : INFINITY;
       if (next < n_items) {
-        m_next = fetch_mask(next);
-        lse_next = fetch_lse(next);
+        km_next = fetch_mask_raw(next);
+        lse_next = fetch_lse_raw(next);
       }
       // ---- P / dS in shared memory are free again once the previous item's gradient MMAs have retired (the
       //      drain warps take those gradients out of TMEM meanwhile)
@@ -415,13 +434,12 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
       const float dsum_s = lds_f32(smem_u32(sD0) + (buf * 128 + row) * 4) / a.drop_scale;
       const float ds_c = a.scale;
       const uint32_t rowkey =
-          a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + qrow) : 0u;
+          a.drop_thr ? attn_drop_rowkey(seed_eff, ((unsigned long long)b * a.nh + h) * a.L + qrow) : 0u;
 
       mbar_wait(bar_s, ph);
       tc_fence_after();
       // ---- P and dS for this thread's (row, every 4th 8-key unit).  P' = P / (1-p) is born scaled (the dropout
       // scale rides in the exponent: lse2 carries -log2(scale)); dropped keys are zeroed in P' and in dP.
-      // The TMEM loads of the NEXT unit are in flight while the current one is processed (ping-pong registers).
       const uint32_t aMask = smem_u32(sMask), aP = smem_u32(sP), adS = smem_u32(sdS);
       // local unit ul of this row's item -> S / dP column: text units 0..7, then the item's prefix units
       auto col_of = [&](int ul) { return ul < 8 ? (blk << 6) + (ul << 3) : NT + blk * a.P8 + ((ul - 8) << 3); };
@@ -451,29 +469,14 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
         w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
         sts_u4(adS + off, w);
       };
-      {
-        uint32_t sa[8], da[8], sb[8], db[8];
-        int u = part;
-        if (u < units) {
-          tmem_ld_32x32b_x8(t_row + TC_S + col_of(u), sa);
-          tmem_ld_32x32b_x8(t_row + TC_DP + col_of(u), da);
-        }
-        for (; u < units; u += 8) {
-          tmem_ld_wait();
-          if (u + 4 < units) {
-            tmem_ld_32x32b_x8(t_row + TC_S + col_of(u + 4), sb);
-            tmem_ld_32x32b_x8(t_row + TC_DP + col_of(u + 4), db);
-          }
-          process_unit(u, sa, da);
-          if (u + 4 < units) {
-            tmem_ld_wait();
-            if (u + 8 < units) {
-              tmem_ld_32x32b_x8(t_row + TC_S + col_of(u + 8), sa);
-              tmem_ld_32x32b_x8(t_row + TC_DP + col_of(u + 8), da);
-            }
-            process_unit(u + 4, sb, db);
-          }
-        }
+      // (one rolled copy of the unit body: 2-3 units per thread; the other 15 warps cover the TMEM load latency)
+#pragma unroll 1
+      for (int u = part; u < units; u += 4) {
+        uint32_t sa[8], da[8];
+        tmem_ld_32x32b_x8(t_row + TC_S + col_of(u), sa);
+        tmem_ld_32x32b_x8(t_row + TC_DP + col_of(u), da);
+        tmem_ld_wait();
+        process_unit(u, sa, da);
       }
       fence_proxy_async_smem();
       tc_fence_before();

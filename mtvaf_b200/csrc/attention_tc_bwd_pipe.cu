@@ -361,22 +361,24 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int units = NS >> 3;
     const float log2_ds = a.drop_thr ? log2f(a.drop_scale) : 0.f;
 
-    // smem key `k`: text row k (k < L64), prefix row k - NT (k >= NT)
-    auto fetch_mask = [&](int item) -> float {
-      if (tid >= NS) return 0.f;
-      const int b = item / a.nh;
-      if (tid < NT) return (tid < a.L) ? (a.key_mask[(long long)b * a.L + tid] != 0 ? 0.f : -10000.0f * kLog2eP) : -INFINITY;
-      return (tid - NT < a.P) ? 0.f : -INFINITY;
+    // smem key `k` = tid: text row k (k < L64), prefix row k - NT (k >= NT).  Only text columns inside the sequence
+    // depend on memory; what is PREFETCHED one item ahead is the raw key-mask word and the raw log-sum-exp: nothing is
+    // computed from them until the next item uses them, so the loads have a whole item to land (see attention_tc_bwd_pair.cu)
+    const bool m_dyn = tid < NT && tid < a.L;
+    const float m_const = tid >= NS ? 0.f : (tid < NT ? -INFINITY : (tid - NT < a.P ? 0.f : -INFINITY));
+    auto fetch_mask_raw = [&](int item) -> long long {
+      return m_dyn ? __ldg(a.key_mask + (long long)(item / a.nh) * a.L + tid) : 1;
     };
-    auto fetch_lse = [&](int item) -> float {
-      const int b = item / a.nh, h = item - b * a.nh;
-      return row_ok ? lse[((long long)b * a.nh + h) * a.L + row] * kLog2eP - log2_ds : INFINITY;
+    auto fetch_lse_raw = [&](int item) -> float {
+      return row_ok ? __ldg(lse + (long long)item * a.L + row) : 0.f;
     };
+    const unsigned long long seed_eff = a.drop_thr ? step_seed(a.seed, a.step) : 0ull;
 
-    float m_next = 0.f, lse_next = 0.f;
+    long long km_next = 1;
+    float lse_next = 0.f;
     if (first < n_items) {
-      m_next = fetch_mask(first);
-      lse_next = fetch_lse(first);
+      km_next = fetch_mask_raw(first);
+      lse_next = fetch_lse_raw(first);
     }
     int il = 0;
     int prev = -1;
@@ -387,11 +389,11 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int next = item + gridDim.x;
       float* sMask = sMask0 + buf * 256;
       // ---- this item's prefetched scalars; the next item's travel while this one is processed
-      if (tid < NS) sMask[tid] = m_next;
-      const float lse2 = lse_next;
+      if (tid < NS) sMask[tid] = m_dyn ? (km_next != 0 ? 0.f : -10000.0f * kLog2eP) : m_const;
+      const float lse2 = row_ok ? lse_next * kLog2eP - log2_ds : INFINITY;
       if (next < n_items) {
-        m_next = fetch_mask(next);
-        lse_next = fetch_lse(next);
+        km_next = fetch_mask_raw(next);
+        lse_next = fetch_lse_raw(next);
       }
       // ---- P / dS in shared memory are free again once the previous item's gradient MMAs have retired (the
       //      drain warps take those gradients out of TMEM meanwhile)
@@ -402,7 +404,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float dsum_s = lds_f32(smem_u32(sD0) + (buf * 128 + row) * 4) / a.drop_scale;
       const float ds_c = a.scale;
       const uint32_t rowkey =
-          a.drop_thr ? attn_drop_rowkey(step_seed(a.seed, a.step), ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
+          a.drop_thr ? attn_drop_rowkey(seed_eff, ((unsigned long long)b * a.nh + h) * a.L + row) : 0u;
 
       mbar_wait(bar_s, ph);
       tc_fence_after();
