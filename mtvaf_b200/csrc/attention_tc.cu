@@ -25,6 +25,10 @@ using namespace ptx;
 constexpr int kFwdThreadsSmall = 256, kFwdThreadsBig = 512;   // 2 / 4 threads per query row
 constexpr float kFwdLog2e = 1.4426950408889634f;
 
+// Single-thread work (TMA and tcgen05.mma issue) sits behind `warp == 0 && elect_one()`, not `tid == 0`: from a branch on the
+// thread index the compiler wraps EVERY tcgen05.mma / TMA instruction in an ELECT / R2UR / BRA.U.ANY loop over the active
+// lanes (~10 instructions and ~55 cycles per MMA); behind elect.sync it issues them back to back (tools/micro/umma_rate.cu:
+// 55 -> 44 cycles per M128 N64 MMA at issue, retire floor 59; in these kernels ~95 -> ~60).
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -94,7 +98,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int r = 0; r < a.L64; r += 64)
       tma_load_2d(sV + (a.P8 + r) * 128, &tmKV, &bars[3], 2 * H + h * 64, b * a.L + a.kt0 + r);
   };
-  if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
+  if (warp == 0 && (int)blockIdx.x < n_items && elect_one()) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
 
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const float sc2 = a.scale * kFwdLog2e;             // fold log2(e): exp(x) = exp2(x * log2e)
@@ -139,7 +143,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       km_next[0] = fetch_raw(bn, dyn0, tid);
       km_next[1] = fetch_raw(bn, dyn1, tid + kFwdThreads);
     }
-    if (tid == 0) {
+    __syncwarp();                                      // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) {
       mbar_wait(&bars[0], ph);
       tc_fence_after();
       // ---- S = Q K^T
@@ -158,7 +163,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&bars[1], ph);
     __syncwarp();
     tc_fence_after();
-    if (tid == 0 && item + (int)gridDim.x < n_items) issue_qk(item + gridDim.x);   // S retired: Q / K are free
+    if (warp == 0 && item + (int)gridDim.x < n_items && elect_one()) issue_qk(item + gridDim.x);   // S retired: Q / K are free
     __syncwarp();
 
     // ---- pass 1: row max of (S / sqrt(d) + mask) * log2 e over this thread's units
@@ -213,7 +218,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       // ---- O = P V
       mbar_wait(&bars[3], ph);                         // V landed (long ago: requested when the previous O retired)
       tc_fence_after();
@@ -232,7 +237,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
     tc_fence_after();
     // V / P of this item are consumed: fetch the next item's V behind the epilogue
-    if (tid == 0 && item + (int)gridDim.x < n_items) issue_v(item + gridDim.x);
+    if (warp == 0 && item + (int)gridDim.x < n_items && elect_one()) issue_v(item + gridDim.x);
     __syncwarp();
 
     // tcgen05.ld is warp-collective (.sync.aligned): EVERY lane issues the loads (rows past L included,
@@ -357,7 +362,7 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
       tma_load_2d(v + a.P8 * 128, &tmKV, &bars[3], 2 * H + h * 64, b * a.L);
     }
   };
-  if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
+  if (warp == 0 && (int)blockIdx.x < n_items && elect_one()) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
 
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const float sc2 = a.scale * kFwdLog2e;
@@ -386,7 +391,8 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
     const int q = row & 63;
     if (tid < n_keys) sMask[tid] = m_dyn ? (km_next != 0 ? 0.f : -10000.0f * kFwdLog2e) : m_const;
     if (item + (int)gridDim.x < n_items) km_next = fetch_raw(item + gridDim.x);
-    if (tid == 0) {
+    __syncwarp();                                      // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) {
       mbar_wait(&bars[0], ph);
       tc_fence_after();
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
@@ -401,7 +407,7 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
     mbar_wait(&bars[1], ph);
     __syncwarp();
     tc_fence_after();
-    if (tid == 0 && item + (int)gridDim.x < n_items) issue_qk(item + gridDim.x);
+    if (warp == 0 && item + (int)gridDim.x < n_items && elect_one()) issue_qk(item + gridDim.x);
     __syncwarp();
 
     float mx = -INFINITY;
@@ -452,7 +458,7 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
     __syncthreads();
     tc_fence_after();
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       mbar_wait(&bars[3], ph);
       tc_fence_after();
       const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
@@ -468,7 +474,7 @@ attn_fwd_tc_pair_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
     mbar_wait(&bars[2], ph);
     __syncwarp();
     tc_fence_after();
-    if (tid == 0 && item + (int)gridDim.x < n_items) issue_v(item + gridDim.x);
+    if (warp == 0 && item + (int)gridDim.x < n_items && elect_one()) issue_v(item + gridDim.x);
     __syncwarp();
 
     const float inv = a.drop_scale / total;

@@ -124,7 +124,7 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
 
   if (warp == 16) {
     // ===================================== control: TMA + MMA issue ======================================
-    if (lane == 0) {
+    if (elect_one()) {                                  // (not `lane == 0`: see attention_tc.cu)
       const uint32_t kv_bytes = (uint32_t)NS * 128u;
       auto load_qkdo = [&](int item, int buf) {
         uint8_t* q = sQ0 + buf * 16384;

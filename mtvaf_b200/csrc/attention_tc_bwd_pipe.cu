@@ -133,7 +133,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 16) {
     // ===================================== control: TMA + MMA issue ======================================
-    if (lane == 0) {
+    if (elect_one()) {                                  // (not `lane == 0`: see attention_tc.cu)
       const uint32_t kv_bytes = (uint32_t)lay.kv_rows * 128u;
       auto load_qkdo = [&](int item, int buf) {
         const int b = item / a.nh, h = item - b * a.nh;
