@@ -192,13 +192,13 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
           mbar_wait(&bar_qk[buf], ph2);
           if (il > 0 && a.P8 > 0) mbar_wait(bar_x, ph ^ 1);
           tc_fence_after();
-#pragma unroll 1
+#pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16_ss(tmem_base + TC_S, q_k + k * 2, k_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
           mbar_wait(&bar_do[buf], ph2);
           mbar_wait(bar_v, ph);
           tc_fence_after();
-#pragma unroll 1
+#pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16_ss(tmem_base + TC_DP, o_k + k * 2, dV_k + k * 2, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(bar_s);
@@ -219,23 +219,23 @@ attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmKV,
           // (A = Q / dO as MN-major operands: rows 64..127 of the M = 128 tile read past the 64 real columns,
           //  finite or not: their output lanes are never stored).  These land in the S columns: P / dS are written
           //  (bar_p), so S is dead.
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 8; ++j)
             umma_f16_ss(tmem_base + TC_DKP, q_mn + j * 128, dS_mn + cp * 1024 + j * 128, idesc_p, j > 0 ? 1u : 0u);
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 8; ++j)
             umma_f16_ss(tmem_base + TC_DVP, o_mn + j * 128, P_mn + cp * 1024 + j * 128, idesc_p, j > 0 ? 1u : 0u);
           umma_commit(bar_gx);
         }
         // dQ[q, d] = sum_key dS[q, key] K[key, d]   (K-major dS: 64-key chunks of 16 KB, 32 B per 16-key step)
-#pragma unroll 1
+#pragma unroll 5
         for (int j = 0; j < ksteps; ++j)
           umma_f16_ss(tmem_base + TC_DQ, dS_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + j * 128, idesc_q, j > 0 ? 1u : 0u);
         // text keys: dK[key, d] = sum_q dS[q, key] Q[q, d] ; dV[key, d] = sum_q P[q, key] dO[q, d]
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 8; ++j)
           umma_f16_ss(tmem_base + TC_DK, dS_mn + j * 128, q_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 8; ++j)
           umma_f16_ss(tmem_base + TC_DV, P_mn + j * 128, o_mn + j * 128, idesc_t, j > 0 ? 1u : 0u);
         umma_commit(bar_g);
