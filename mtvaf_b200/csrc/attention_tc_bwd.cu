@@ -192,7 +192,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float m_next = 0.f, lse_next = 0.f;
   uint4 o0n = make_uint4(0, 0, 0, 0), o1n = o0n;
   if (first < n_items) {
-    if (tid == 0) { load_qk(first, 0); load_do(first); load_v(first); }
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) { load_qk(first, 0); load_do(first); load_v(first); }
     m_next = fetch_mask(first);
     lse_next = fetch_lse(first);
     fetch_o(first, o0n, o1n);
@@ -212,7 +213,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (tid < a.N16) sMask[tid] = m_next;
     const float lse2 = lse_next;
     const uint4 o0 = o0n, o1 = o1n;
-    if (tid == 0) {
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) {
       // the other Q/K buffer was last read by the previous item's MMAs (retired): request the next item's tiles
       if (nbuf == 2 && next < n_items) load_qk(next, buf ^ 1);
       // ---- S = Q K^T -> cols [0,N16) ; dP = dO V^T -> cols [256, 256+N16)
@@ -265,7 +267,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bar_s, ph);
     __syncwarp();
     tc_fence_after();
-    if (tid == 0 && next < n_items) load_v(next);      // dP has retired: V is free
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && next < n_items && elect_one()) load_v(next);      // dP has retired: V is free
 
     // ---- P and dS for this thread's (row, every 4th 8-key unit).  P' = P / (1-p) is born scaled (the dropout scale
     // rides in the exponent: lse2 already carries -log2(scale)); dropped keys are zeroed in P' and in dP.
@@ -305,7 +308,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
 
-    if (tid == 0) {
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) {
       const uint32_t adS = smem_u32(sdS), aP = smem_u32(sP), aQ = smem_u32(sQ), adO = smem_u32(sdO),
                      aK = smem_u32(sK);
       // dQ[q, d] = sum_key dS[q,key] K[key,d]
@@ -335,7 +339,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
     tc_fence_after();
     // every operand tile of this item has been consumed: fetch the next item's while the gradients drain
-    if (tid == 0 && next < n_items) {
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && next < n_items && elect_one()) {
       load_do(next);
       if (nbuf == 1) load_qk(next, 0);
     }

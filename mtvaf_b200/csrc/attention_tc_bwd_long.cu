@@ -126,7 +126,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int q0 = qg * 256;                             // first query row of the group
     const int nq = min(2, nq_all - qg * 2);              // query tiles in this group
     // ---- group prologue: Q / dO tiles by TMA; key masks, log-sum-exp and D_q = rowsum(dO o O) into shared memory
-    if (tid == 0) {
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) {
       mbar_arrive_expect_tx(bar_q, (uint32_t)nq * 2u * 16384u);
       for (int qt = 0; qt < nq; ++qt) {
         tma_load_2d(sQ + qt * 16384, &tmQ, bar_q, h * 64, b * a.L + q0 + qt * 128);
@@ -179,7 +180,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool prefix_block = has_prefix && kb == 0;
       const int NB = prefix_block ? (a.P8 + 15) / 16 * 16 : 128;     // MMA N of S / dP, K extent of dQ
       const int units = NB >> 3;
-      if (tid == 0) {
+      __syncwarp();                                    // elect.sync needs the whole warp
+      if (warp == 0 && elect_one()) {
         // K / V of the previous block were last read by MMAs that have retired (bar_g awaited by everyone)
         if (prefix_block) {
           mbar_arrive_expect_tx(bar_kv, 2u * (uint32_t)a.P8 * 128u);
@@ -198,7 +200,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       for (int qt = 0; qt < nq; ++qt) {
         const int q = q0 + qt * 128 + row;
-        if (tid == 0) {
+        __syncwarp();                                    // elect.sync needs the whole warp
+        if (warp == 0 && elect_one()) {
           const uint32_t aQ = smem_u32(sQ + qt * 16384), aK = smem_u32(sK), adO = smem_u32(sdO + qt * 16384),
                          aV = smem_u32(sV);
           const uint32_t idesc = make_idesc_bf16(128, NB, false, false);
@@ -259,7 +262,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        __syncwarp();                                    // elect.sync needs the whole warp
+        if (warp == 0 && elect_one()) {
           const uint32_t adS = smem_u32(sdS), aP = smem_u32(sP), aQ = smem_u32(sQ + qt * 16384),
                          adO = smem_u32(sdO + qt * 16384), aK = smem_u32(sK);
           // dQ[tile][q, d] += sum_key dS[q, key] K[key, d]

@@ -120,7 +120,8 @@ pairwise_gram_tc_kernel(const float* __restrict__ T, long long ld, int L, int R,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
+    __syncwarp();                                    // elect.sync needs the whole warp
+    if (warp == 0 && elect_one()) {
       const uint32_t aAh = smem_u32(st), aAl = aAh + kTile;
       const uint32_t aBh = diag ? aAh : aAh + 2 * kTile, aBl = diag ? aAl : aAh + 3 * kTile;
 #pragma unroll
