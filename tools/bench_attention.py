@@ -1,5 +1,6 @@
 """Prefix-attention kernels alone at one shape: `python tools/bench_attention.py [B L P]` -> us per launch (CUDA events
-around 20 launches on the launch stream, inputs (3 x B x L x 768 bf16) larger than L2 at the bench shape)."""
+around 20 launches on the launch stream, inputs (3 x B x L x 768 bf16) larger than L2).  The bench shape is `512 128 16`;
+the default `512 64 16` is the short-text shape that runs two (batch, head) items per tile."""
 import os
 import sys
 import torch
